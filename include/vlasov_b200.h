@@ -1,0 +1,222 @@
+/*
+ * vlasov_b200.h -- C ABI of libvlasov_b200.so
+ *
+ * B200-native (sm_100a, fp64) implementation of the particle hot path of
+ * JuliaPlasma/VlasovMethods.jl: one step of the 1d1v spline particle-in-cell
+ * loop (Vlasov-Poisson) and the spline velocity-space projection + right-hand
+ * side of the Lenard-Bernstein collision operators.
+ *
+ * The reference has no FFI: its boundary is Julia multiple dispatch.  Each entry
+ * point below names the reference call site it replaces (paths relative to the
+ * reference repo root); INTEGRATION.md shows the `ccall` bodies a maintainer
+ * would add behind the unchanged Julia signatures.
+ *
+ * Conventions
+ *  - every function returns a vm_status (0 = OK); the message of the last
+ *    failure is returned by vm_last_error(ctx) (ctx may be NULL for failures of
+ *    vm_ctx_create).  No exception crosses this boundary.
+ *  - the library owns all device memory behind opaque handles; host pointers
+ *    are borrowed for the duration of the call only.
+ *  - a vm_ctx is bound to ONE device and ONE host thread at a time (the
+ *    reference is single-threaded).  Calls enqueue work on the context's stream
+ *    and return; any call that hands data back to the host synchronises.
+ *  - multi-GPU: one process (one vm_ctx) per GPU; particles are sharded, the
+ *    deposited grid is all-reduced over NCCL inside vm_field_solve /
+ *    vm_vproject, the small solves are replicated (bit-identical on all ranks).
+ *  - Float64 only, 1d1v only.  There is NO CPU fallback: without a CUDA device
+ *    vm_ctx_create fails with VM_ERR_NO_DEVICE.
+ */
+#ifndef VLASOV_B200_H
+#define VLASOV_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VM_ABI_VERSION 1
+
+typedef struct vm_ctx vm_ctx;
+typedef struct vm_particles vm_particles;
+typedef struct vm_field vm_field;
+typedef struct vm_vspline vm_vspline;
+
+typedef enum vm_status {
+    VM_OK = 0,
+    VM_ERR_INVALID = 1,      /* bad argument */
+    VM_ERR_CUDA = 2,         /* CUDA runtime failure (message has the detail) */
+    VM_ERR_NOMEM = 3,
+    VM_ERR_NCCL = 4,
+    VM_ERR_UNSUPPORTED = 5,  /* e.g. spline order outside 2..6 */
+    VM_ERR_NO_DEVICE = 6     /* no CUDA device: the library has no CPU path */
+} vm_status;
+
+/* ---------------------------------------------------------------- context */
+int vm_abi_version(void);
+
+/* Create a context on CUDA device `device` (ordinal). */
+int vm_ctx_create(int device, vm_ctx** out);
+int vm_ctx_destroy(vm_ctx* ctx);
+const char* vm_last_error(vm_ctx* ctx);
+/* Block until all work enqueued on the context has finished. */
+int vm_sync(vm_ctx* ctx);
+int vm_ctx_device_info(vm_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor,
+                       size_t* free_bytes, size_t* total_bytes);
+/* Tuning knobs (defaults are chosen from the device and problem size).
+ * key: "ctas_per_sm", "threads_per_cta", "replicas" (0 = auto), "use_graph". */
+int vm_ctx_set_tuning(vm_ctx* ctx, const char* key, int value);
+
+/* Multi-GPU, one process per GPU.  Rank 0 obtains a 128-byte NCCL unique id
+ * and distributes it by any host channel (MPI.jl, torch.distributed, a file). */
+int vm_comm_unique_id(void* out128);
+int vm_ctx_comm_init(vm_ctx* ctx, int rank, int nranks, const void* id128);
+int vm_ctx_comm_info(vm_ctx* ctx, int* rank, int* nranks);
+
+/* Device timing on the context's own stream (CUDA events), slots 0..15. */
+int vm_event_record(vm_ctx* ctx, int slot);
+int vm_event_elapsed_ms(vm_ctx* ctx, int slot_start, int slot_stop, double* ms);
+/* Number of kernels this context has launched so far. */
+unsigned long long vm_launch_count(vm_ctx* ctx);
+
+/* ------------------------------------------------------------- particles --
+ * Replaces ParticleDistribution{1,1} (src/distributions/particle_distribution.jl:2-24),
+ * a ParticleMethods.ParticleList over a 3xN Float64 matrix [x;v;w] (AoS).
+ * Device layout: three SoA arrays x[N], v[N], w[N]. */
+int vm_particles_create(vm_ctx* ctx, long n, vm_particles** out);
+int vm_particles_destroy(vm_particles* p);
+long vm_particles_size(vm_particles* p);
+/* z3xn: column-major 3xN matrix = the memory of ParticleList.z with the weight row. */
+int vm_particles_upload_aos(vm_particles* p, const double* z3xn);
+int vm_particles_download_aos(vm_particles* p, double* z3xn);
+/* Any of x, v, w may be NULL (left untouched). */
+int vm_particles_upload_soa(vm_particles* p, const double* x, const double* v, const double* w);
+int vm_particles_download_soa(vm_particles* p, double* x, double* v, double* w);
+int vm_particles_copy(vm_particles* dst, vm_particles* src);
+
+/* Device-side synthetic loads reproducing the *distributions* of
+ * src/examples/*.jl (the reference draws from Julia's unseeded global RNG, so
+ * streams cannot match).  Counter-based Philox4x32-10 keyed by
+ * (seed, global particle index): the load is independent of the sharding.
+ * first_index/total_n: this shard holds particles first_index .. first_index+n-1
+ * of a global population of total_n. */
+typedef enum vm_fill_kind {
+    VM_FILL_NORMAL = 0,          /* normal.jl:10-36    params: xlo, xhi                     */
+    VM_FILL_BUMP_ON_TAIL = 1,    /* bumpontail.jl:43-75 params: eps, kappa, alpha, sigma, v0 */
+    VM_FILL_DOUBLE_MAXWELLIAN = 2,/* doublemaxwellian.jl:9-39 params: xlo, xhi, shift         */
+    VM_FILL_UNIFORM = 3,         /* uniform.jl:10-33   params: xlo, xhi, vlo, vhi           */
+    VM_FILL_SHIFTED_NORMAL_V = 4,/* shiftednormalv.jl  params: xlo, xhi, shift              */
+    VM_FILL_SHIFTED_UNIFORM = 5, /* shifteduniform.jl  params: xlo, xhi, vlo, vhi, shift    */
+    VM_FILL_LANDAU = 6           /* (1+eps cos kx) Maxwellian  params: eps, kappa           */
+} vm_fill_kind;
+int vm_particles_fill(vm_particles* p, int kind, const double* params, int nparams,
+                      unsigned long long seed, long first_index, long total_n);
+
+/* ----------------------------------------------------------------- field --
+ * Replaces Potential(PeriodicBasisBSplineKit(domain, order, nknot))
+ * (scripts/vlasov_poisson.jl:21) and the legacy PoissonSolverPBSplines(p, nh, L)
+ * (scripts/bump_on_tail.jl:38).  n_basis periodic B-splines of order `order`
+ * (= degree + 1) on [a,b).  index_shift: a particle in cell c touches basis
+ * indices (c + j + index_shift) mod n_basis, j = 0..order-1 (a pure rotation of
+ * the coefficient vectors; BSplineKit's periodic basis uses order/2 - order + 1). */
+int vm_field_create(vm_ctx* ctx, double a, double b, int order, int n_basis, int index_shift,
+                    vm_field** out);
+int vm_field_destroy(vm_field* f);
+int vm_field_get_rhs(vm_field* f, double* host_n);            /* potential.rhs            */
+int vm_field_get_coefficients(vm_field* f, double* host_n);   /* potential.coefficients   */
+/* ExternalField (src/electric_field.jl:66-69): prescribe phi, no deposit/solve. */
+int vm_field_set_coefficients(vm_field* f, const double* host_n);
+/* Circulant stencils (centre, +1, ..., +order-1) of the mass and stiffness matrices. */
+int vm_field_get_stencils(vm_field* f, double* mass_k, double* stiff_k);
+
+typedef enum vm_deposit_mode {
+    VM_DEPOSIT_DETERMINISTIC = 0, /* warp-private replicas, in-warp sort-by-cell segmented
+                                     reduce in lane order, fixed-order tree across warps/CTAs:
+                                     bit-reproducible run to run */
+    VM_DEPOSIT_ATOMIC = 1         /* warp-aggregated shared-memory atomics + global fp64 RED */
+} vm_deposit_mode;
+
+/* projection!(potential, dist): src/projections/potential.jl:2-22.
+ * rhs_i = sum_p w_p B_i(x_p) over this rank's particles (local partial). */
+int vm_deposit(vm_field* f, vm_particles* p, int mode);
+/* PoissonSolvers.update!(potential) (src/models/vlasov_poisson.jl:14),
+ * update!(::PoissonField, x, w, t) (src/electric_field.jl:45): all-reduce rhs over
+ * the ranks, then solve S phi = rhs - mean(rhs), sum(phi) = 0. */
+int vm_field_solve(vm_field* f);
+/* energy(::PoissonField) = 1/2 phi' S phi (src/electric_field.jl:47). */
+int vm_field_energy(vm_field* f, double* W);
+/* efield!(f, e, x) (src/electric_field.jl:43) with ScaledField's 1/chi^2 (:26-29):
+ * e_host[p] = -phi'(x_p) * inv_chi2.   e_host may be NULL (result stays on device). */
+int vm_gather_E(vm_field* f, vm_particles* p, double* e_host, double inv_chi2);
+/* phi'(x) at arbitrary host points (Potential functor phi(x, Derivative(1)),
+ * src/models/vlasov_poisson.jl:27,48,65); deriv = 0 evaluates phi itself. */
+int vm_field_eval(vm_field* f, const double* x_host, long n, int deriv, double* out_host);
+
+/* s_advection! (src/models/vlasov_poisson.jl:53-58): x += dt * v. */
+int vm_vp_drift(vm_particles* p, double dt);
+/* s_acceleration! without the potential update (:63-66): v += dt * scale * phi'(x);
+ * the reference uses scale = -1 (new API) or -1/chi^2 (legacy). */
+int vm_vp_kick(vm_field* f, vm_particles* p, double dt, double scale);
+
+typedef enum vm_run_flags {
+    VM_RUN_SPLIT_KICK = 1,    /* two half kicks B(dt/2)B(dt/2) like GeometricIntegrators' Strang
+                                 composition (new API); default is one B(dt) (legacy loop)       */
+    VM_RUN_FROZEN_FIELD = 2,  /* field_source = model_ics: never re-deposit; reproduces the
+                                 frozen-field quirk of the new API                   */
+    VM_RUN_ATOMIC_DEPOSIT = 4,/* use VM_DEPOSIT_ATOMIC inside the fused step                     */
+    VM_RUN_UNFUSED = 8        /* separate drift / deposit / solve / kick passes (for A/B tests)  */
+} vm_run_flags;
+
+/* nsteps Strang steps A(dt/2) B(dt) A(dt/2) with self-consistent field:
+ * integrate!(SplittingMethod) (src/methods/splitting.jl:40-43) and the body of
+ * integrate_vp! (src/vlasov_poisson.jl:94-115) incl. ScaledField: effective step
+ * dt*chi, E/chi^2.  Consecutive steps are fused into one particle pass per step
+ * (gather E -> kick -> drift -> deposit).  State is at integer time on return.
+ * diag_every > 0: every diag_every-th step (and step 0) append a row
+ * [W, K, M, sum_w] to diag_host (save_timestep!, src/vlasov_poisson.jl:58-67);
+ * diag_host must hold nsteps/diag_every + 1 rows.  diag_every = 0: no diagnostics. */
+int vm_vp_run(vm_field* f, vm_particles* p, double dt, int nsteps, int diag_every, int flags,
+              double chi, double* diag_host);
+
+/* [W, K, M, sum_w] for the current state (deposit + solve + reductions). */
+int vm_diagnostics(vm_field* f, vm_particles* p, double chi, double* out4);
+
+/* --------------------------------------------------------------- vspline --
+ * Replaces SplineDistribution(1, 1, nknots, order, domain, :Dirichlet)
+ * (src/distributions/spline_distribution.jl:23-36): clamped B-splines on
+ * LinRange(vmin, vmax, nknots), bc = 1: homogeneous Dirichlet recombination
+ * (nknots + order - 4 functions), bc = 0: parent basis (nknots + order - 2). */
+int vm_vspline_create(vm_ctx* ctx, double vmin, double vmax, int nknots, int order, int bc,
+                      vm_vspline** out);
+int vm_vspline_destroy(vm_vspline* s);
+int vm_vspline_size(vm_vspline* s);                                  /* length(basis)  */
+int vm_vspline_get_coefficients(vm_vspline* s, double* host_nv);      /* sdist.coefficients */
+int vm_vspline_set_coefficients(vm_vspline* s, const double* host_nv);
+int vm_vspline_get_rhs(vm_vspline* s, double* host_nv);
+int vm_vspline_get_mass_matrix(vm_vspline* s, double* host_nv_x_nv);  /* galerkin_matrix   */
+/* projection(v, dist, sdist): src/projections/distribution.jl:35-55.
+ * Uses the particles' v and w arrays. */
+int vm_vproject(vm_vspline* s, vm_particles* p);
+/* spline.(v), (Derivative(1)*spline).(v) at host points (either output may be NULL). */
+int vm_vspline_eval(vm_vspline* s, const double* v_host, long n, double* f_host, double* df_host);
+/* compute_f_densities / compute_df_densities (src/projections/density.jl:6-20):
+ * out5 = [sum f, sum v f, sum v^2 f, sum f', sum v f'] (unweighted particle sums,
+ * all ranks) and A = [A1, A2] of compute_coefficients
+ * (src/models/lenard_bernstein_conservative.jl:11-21). */
+int vm_vmoments(vm_vspline* s, vm_particles* p, double* out5, double* A2);
+/* LB_rhs! (src/models/lenard_bernstein.jl:20-30), conservative = 0, and
+ * CLB_rhs! (src/models/lenard_bernstein_conservative.jl:24-36), conservative = 1:
+ * projection + (moments) + vdot_p = -nu (f' + (A1 + A2 v) f).
+ * vdot_host may be NULL; the result is kept on the device either way. */
+int vm_lb_rhs(vm_vspline* s, vm_particles* p, double nu, int conservative, double* vdot_host);
+/* nsteps RK438 (3/8-rule) steps of the velocity ODE: the loop of
+ * run!(::GeometricIntegrator) (src/methods/geometric_integrator.jl:31-35).
+ * diag_every > 0: rows [t, sum_p v_p, sum_p v_p^2] (scripts/
+ * lenard_bernstein_conservative.jl:49-50) at step 0 and every diag_every-th step. */
+int vm_lb_rk438_run(vm_vspline* s, vm_particles* p, double dt, int nsteps, double nu,
+                    int conservative, int diag_every, double* diag_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VLASOV_B200_H */

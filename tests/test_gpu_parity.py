@@ -1,0 +1,385 @@
+"""GPU parity tests: CUDA path (through the C ABI) vs the CPU oracle on the same seeded inputs.
+
+Tolerance (north star): relative <= 1e-12 on deposited moments and fields, measured against the
+max-norm of the reference vector; trajectories after several steps <= 1e-11 absolute (O(1) values).
+"""
+import math
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-12
+
+
+def relmax(a, b):
+    return np.max(np.abs(np.asarray(a) - np.asarray(b))) / max(np.max(np.abs(b)), 1e-300)
+
+
+@pytest.fixture(scope="module")
+def ctx(vm):
+    c = vm.Context(0)
+    yield c
+    c.close()
+
+
+def make_particles(rng, npart, a, b, spread=3.0):
+    L = b - a
+    x = rng.uniform(a - spread * L, b + spread * L, npart)
+    v = rng.standard_normal(npart)
+    w = rng.uniform(0.5, 1.5, npart) * L / npart
+    return x, v, w
+
+
+# ------------------------------------------------------------------ deposit --
+@pytest.mark.parametrize("k", [2, 3, 4, 5, 6])
+@pytest.mark.parametrize("n", [16, 33, 64, 200, 1024])
+def test_deposit_matches_oracle(vm, oracle, ctx, rng, k, n):
+    a, b = -1.0, 2 * math.pi / 0.3 - 1.0
+    npart = 50001
+    x, v, w = make_particles(rng, npart, a, b)
+    shift = oracle.bspline_shift_bsplinekit(k)
+    ref = oracle.deposit_periodic(x, w, a, b, n, k, shift)
+    fld = vm.DeviceField(ctx, a, b, k, n, shift)
+    p = vm.DeviceParticles(ctx, npart)
+    p.upload(x, v, w)
+    for mode in (0, 1):
+        fld.deposit(p, mode)
+        got = fld.rhs
+        assert relmax(got, ref) <= RTOL, (k, n, mode)
+        assert abs(got.sum() - w.sum()) <= 1e-13 * w.sum()
+
+
+def test_deposit_deterministic_bitwise(vm, ctx, rng):
+    a, b, n, k = 0.0, 1.0, 128, 4
+    npart = 400003
+    x, v, w = make_particles(rng, npart, a, b)
+    fld = vm.DeviceField(ctx, a, b, k, n, 0)
+    p = vm.DeviceParticles(ctx, npart)
+    p.upload(x, v, w)
+    runs = []
+    for _ in range(4):
+        fld.deposit(p, 0)
+        runs.append(fld.rhs.tobytes())
+    assert all(r == runs[0] for r in runs)
+    # lane-private variant (n small)
+    fld2 = vm.DeviceField(ctx, a, b, k, 16, 0)
+    runs = []
+    for _ in range(4):
+        fld2.deposit(p, 0)
+        runs.append(fld2.rhs.tobytes())
+    assert all(r == runs[0] for r in runs)
+
+
+@pytest.mark.parametrize("replicas", [1, 2, 4, 8, 16, 32])
+def test_deposit_all_replica_variants(vm, oracle, rng, replicas):
+    c = vm.Context(0)
+    c.set_tuning("replicas", replicas)
+    a, b, n, k = 0.0, 3.0, 24, 4
+    x, v, w = make_particles(rng, 30000, a, b)
+    ref = oracle.deposit_periodic(x, w, a, b, n, k, 0)
+    fld = vm.DeviceField(c, a, b, k, n, 0)
+    p = vm.DeviceParticles(c, x.size)
+    p.upload(x, v, w)
+    fld.deposit(p, 0)
+    assert relmax(fld.rhs, ref) <= RTOL
+    fld.close(); p.close(); c.close()
+
+
+def test_deposit_edge_cases(vm, oracle, ctx, rng):
+    a, b, n, k = 0.0, 1.0, 16, 3
+    fld = vm.DeviceField(ctx, a, b, k, n, 0)
+    # empty
+    p0 = vm.DeviceParticles(ctx, 0)
+    fld.deposit(p0, 0)
+    assert np.all(fld.rhs == 0)
+    # single particle, exactly on knots and domain ends
+    for xv in [0.0, 1.0, 0.5, 1.0 - 1e-17, -1e-17, 0.0625, 7.0, -7.0]:
+        p1 = vm.DeviceParticles(ctx, 1)
+        p1.upload(np.array([xv]), np.array([0.0]), np.array([2.5]))
+        fld.deposit(p1, 0)
+        ref = oracle.deposit_periodic(np.array([xv]), np.array([2.5]), a, b, n, k, 0)
+        assert np.max(np.abs(fld.rhs - ref)) <= 1e-14, xv
+    # all particles in one cell (maximum collision pressure)
+    x = rng.uniform(0.5, 0.5 + 1.0 / n, 100000)
+    w = np.full(x.size, 1.0 / x.size)
+    p = vm.DeviceParticles(ctx, x.size)
+    p.upload(x, np.zeros_like(x), w)
+    for nn in (16, 256):
+        f2 = vm.DeviceField(ctx, a, b, 4, nn, 0)
+        for mode in (0, 1):
+            f2.deposit(p, mode)
+            assert relmax(f2.rhs, oracle.deposit_periodic(x, w, a, b, nn, 4, 0)) <= RTOL
+
+
+# ------------------------------------------------------- solve / gather / W --
+@pytest.mark.parametrize("k,n", [(3, 16), (4, 16), (4, 100), (5, 64), (4, 512)])
+def test_solve_gather_energy(vm, oracle, ctx, rng, k, n):
+    a, b = 0.0, 2 * math.pi / 0.5
+    npart = 40000
+    L = b - a
+    u = rng.uniform(0, 1, npart)
+    x = u * L + 0.05 / 0.5 * np.sin(0.5 * u * L)       # mildly perturbed
+    v = rng.standard_normal(npart)
+    w = np.full(npart, L / npart)
+    fld = vm.DeviceField(ctx, a, b, k, n, 0)
+    p = vm.DeviceParticles(ctx, npart)
+    p.upload(x, v, w)
+    fld.deposit(p, 0)
+    fld.solve()
+    S = oracle.periodic_stiffness(a, b, n, k, 0)
+    M = oracle.periodic_mass(a, b, n, k, 0)
+    assert relmax(fld.stiffness_matrix(), S) <= 1e-13
+    assert relmax(fld.mass_matrix(), M) <= 1e-13
+    rhs = oracle.deposit_periodic(x, w, a, b, n, k, 0)
+    phi = oracle.poisson_solve(S, rhs)
+    assert relmax(fld.coefficients, phi) <= RTOL
+    assert abs(fld.coefficients.sum()) <= 1e-12 * np.abs(phi).sum()
+    dphi = oracle.eval_dphi(x, a, b, n, k, 0, phi)
+    E = fld.gather_E(p, 1.0)
+    assert relmax(E, -dphi) <= RTOL
+    E2 = fld.gather_E(p, 0.25)
+    assert relmax(E2, -0.25 * dphi) <= RTOL
+    xs = rng.uniform(a - L, b + L, 333)
+    assert relmax(fld.eval(xs, 1), oracle.eval_dphi(xs, a, b, n, k, 0, phi)) <= RTOL
+    W = fld.energy()
+    Wref = oracle.field_energy(S, phi)
+    assert abs(W - Wref) <= 1e-11 * abs(Wref)
+
+
+def test_gather_is_pure_function_of_phi(vm, ctx, rng):
+    """Restated test/electric_field_tests.jl:37,46: PoissonField == ExternalField fed the same phi, bitwise."""
+    nh, pdeg, L = 16, 3, 2 * math.pi
+    x = rng.uniform(0, L, 100); w = np.full(100, L / 100)
+    poisson = vm.PoissonSolverPBSplines(pdeg, nh, L, ctx=ctx)
+    pf = vm.PoissonField(poisson)
+    ep = pf(x, w, 0.0)
+    phi = np.column_stack([poisson.ϕ, rng.uniform(size=(nh, 10))])
+    e2 = vm.ExternalField(poisson, phi, 0.1)
+    ef2 = e2(x, w, 0.0)
+    assert np.array_equal(ep, ef2)
+    s1 = vm.ScaledField(pf, 1.0)
+    assert np.array_equal(ep, s1(x, w, 0.0))
+    s2 = vm.ScaledField(e2, 1.0)
+    assert np.array_equal(ep, s2(x, w, 0.0))
+    assert np.any(ep != 0)
+
+
+# -------------------------------------------------------------- time steps ---
+@pytest.mark.parametrize("k,n,chi", [(4, 16, 1.0), (3, 16, 1.0), (5, 40, 1.0), (4, 128, 0.7)])
+def test_vp_run_matches_legacy_loop(vm, oracle, ctx, rng, k, n, chi):
+    kappa = 0.3
+    a, b = 0.0, 2 * math.pi / kappa
+    npart = 30001
+    x = rng.uniform(a, b, npart); v = rng.standard_normal(npart); w = np.full(npart, (b - a) / npart)
+    S = oracle.periodic_stiffness(a, b, n, k, 0)
+    nt, nsave, dt = 12, 3, 0.1
+    xo, vo = x.copy(), v.copy()
+    dref, phiref = oracle.integrate_vp(xo, vo, w, dt, chi, nt, nsave, a, b, n, k, 0, S, want_phi=True)
+    fld = vm.DeviceField(ctx, a, b, k, n, 0)
+    p = vm.DeviceParticles(ctx, npart)
+    for flags in (0, 8, 4):      # fused, unfused, fused with atomic deposit
+        p.upload(x, v, w)
+        diag = fld.run(p, dt, nt, nsave, flags, chi)
+        xg, vg, _ = p.download(w=False)
+        assert np.max(np.abs(xg - xo)) <= 1e-11, flags
+        assert np.max(np.abs(vg - vo)) <= 1e-11, flags
+        assert diag.shape == (nt // nsave + 1, 4)
+        assert np.allclose(diag[:, :3], dref, rtol=1e-10, atol=1e-13), flags
+        assert np.allclose(diag[:, 3], w.sum(), rtol=1e-13)
+        assert relmax(fld.coefficients, phiref[-1]) <= 1e-10
+
+
+def test_vp_run_matches_strang_new_api(vm, oracle, ctx, rng):
+    """New-API Strang A(dt/2) B(dt/2) B(dt/2) A(dt/2), self-consistent and frozen-field."""
+    a, b, n, k = 0.0, 1.0, 16, 3
+    npart = 10000
+    z = rng.standard_normal(npart)
+    X = math.ceil(np.max(np.abs(z)))
+    x = (z + X) / (2 * X); v = rng.standard_normal(npart); w = np.full(npart, 1.0 / npart)
+    shift = oracle.bspline_shift_bsplinekit(k)
+    S = oracle.periodic_stiffness(a, b, n, k, shift)
+    fld = vm.DeviceField(ctx, a, b, k, n, shift)
+    p = vm.DeviceParticles(ctx, npart)
+    # self-consistent
+    xo, vo = x.copy(), v.copy()
+    for _ in range(7):
+        oracle.vp_strang_step(xo, vo, w, 0.1, a, b, n, k, shift, S)
+    p.upload(x, v, w)
+    fld.run(p, 0.1, 7, 0, 1, 1.0)
+    xg, vg, _ = p.download(w=False)
+    assert np.max(np.abs(xg - xo)) <= 1e-11 and np.max(np.abs(vg - vo)) <= 1e-11
+    # frozen at the initial particles
+    xo, vo = x.copy(), v.copy()
+    for _ in range(7):
+        oracle.vp_strang_step(xo, vo, w, 0.1, a, b, n, k, shift, S, x_src=x)
+    p.upload(x, v, w)
+    fld.deposit(p, 0); fld.solve()
+    fld.run(p, 0.1, 7, 0, 1 | 2, 1.0)
+    xg, vg, _ = p.download(w=False)
+    assert np.max(np.abs(xg - xo)) <= 1e-11 and np.max(np.abs(vg - vo)) <= 1e-11
+
+
+def test_mirror_splitting_method(vm, oracle, ctx, rng, tmp_path):
+    """scripts/vlasov_poisson.jl through the mirrored API (default config: N=1e4, 16 knots, order 3)."""
+    vm.set_default_context(ctx)
+    npart, nknot, order, tstep = 10000, 16, 3, 0.1
+    dist = vm.initialize_(vm.ParticleDistribution(1, 1, npart), vm.NormalDistribution(), seed=3)
+    x0 = dist.particles.x[0].copy(); v0 = dist.particles.v[0].copy(); w0 = dist.particles.w[0].copy()
+    assert x0.min() >= 0 and x0.max() <= 1 and abs(w0.sum() - 1) < 1e-12 and abs(v0.std() - 1) < 0.05
+    potential = vm.Potential(vm.PeriodicBasisBSplineKit((0.0, 1.0), order, nknot))
+    model = vm.VlasovPoisson(dist, potential)
+    integ = vm.SplittingMethod(model, (0.0, 1.0), tstep)
+    out = tmp_path / "vp.npz"
+    vm.run_(integ, str(out), save_every=5)
+    z = np.load(out)["z"]
+    assert z.shape == (2, npart, 3)
+    shift = potential.basis.index_shift
+    S = oracle.periodic_stiffness(0.0, 1.0, nknot, order, shift)
+    xo, vo = x0.copy(), v0.copy()
+    for _ in range(10):
+        oracle.vp_strang_step(xo, vo, w0, tstep, 0.0, 1.0, nknot, order, shift, S)
+    assert np.max(np.abs(dist.particles.x[0] - xo)) <= 1e-11
+    assert np.max(np.abs(dist.particles.v[0] - vo)) <= 1e-11
+    assert np.array_equal(z[0, :, -1], dist.particles.x[0])
+    vm.set_default_context(None)
+
+
+def test_particles_aos_roundtrip_and_kick_drift(vm, oracle, ctx, rng):
+    npart = 12347
+    z = rng.standard_normal((npart, 3))
+    p = vm.DeviceParticles(ctx, npart)
+    p.upload_aos(z)
+    x, v, w = p.download()
+    assert np.array_equal(x, z[:, 0]) and np.array_equal(v, z[:, 1]) and np.array_equal(w, z[:, 2])
+    assert np.array_equal(p.download_aos(), z)
+    p.drift(0.25)
+    assert np.array_equal(p.download()[0], z[:, 0] + 0.25 * z[:, 1])
+    fld = vm.DeviceField(ctx, 0.0, 1.0, 4, 16, 0)
+    phi = rng.standard_normal(16); phi -= phi.mean()
+    fld.coefficients = phi
+    xcur = p.download()[0]
+    fld.kick(p, 0.1, -1.0)
+    vref = z[:, 1] - 0.1 * oracle.eval_dphi(xcur, 0.0, 1.0, 16, 4, 0, phi)
+    assert np.max(np.abs(p.download()[1] - vref)) <= 1e-12 * np.max(np.abs(vref))
+
+
+# ---------------------------------------------------------------- v-space ----
+@pytest.mark.parametrize("nknots,k", [(41, 4), (41, 3), (17, 5), (129, 4), (9, 2), (300, 6)])
+def test_vspline_projection_and_rhs(vm, oracle, ctx, rng, nknots, k):
+    a, b = -10.0, 10.0
+    npart = 60001
+    v = np.concatenate([rng.standard_normal(npart - 7) * 2.0 + 0.3, [-9.99, 9.99, 10.0, -10.0, 10.5, -11.0, 0.0]])
+    w = rng.uniform(0.5, 1.5, npart) / npart
+    M = oracle.dirichlet_mass(a, b, nknots, k)
+    vs = vm.DeviceVSpline(ctx, a, b, nknots, k, 1)
+    assert vs.nv == nknots + k - 4
+    assert relmax(vs.mass_matrix(), M) <= 1e-13
+    p = vm.DeviceParticles(ctx, npart)
+    p.upload(np.zeros(npart), v, w)
+    vs.project(p)
+    coef, rhs = oracle.vproject(v, w, a, b, nknots, k, M)
+    assert relmax(vs.rhs, rhs) <= RTOL
+    assert relmax(vs.coefficients, coef) <= 1e-11
+    pts = np.concatenate([rng.uniform(a, b, 500), [a, b, a - 1, b + 1]])
+    f, df = vs.eval(pts)
+    fr, dfr = oracle.vspline_eval(pts, a, b, nknots, k, coef)
+    assert relmax(f, fr) <= 1e-11 and relmax(df, dfr) <= 1e-10
+    m5, A = vs.moments(p)
+    m5r = oracle.vmoments(v, a, b, nknots, k, coef)
+    assert np.allclose(m5, m5r, rtol=1e-10, atol=1e-9 * np.max(np.abs(m5r)))
+    for cons in (False, True):
+        vdot = vs.lb_rhs(p, 1.3, cons)
+        ref, _, Aref = oracle.lb_rhs(v, w, a, b, nknots, k, M, 1.3, cons)
+        assert relmax(vdot, ref) <= 1e-9, (cons,)
+        if cons and k >= 3:
+            assert np.allclose(A, Aref, rtol=1e-8)
+
+
+def test_clb_rk438_matches_oracle_and_conserves(vm, oracle, ctx, rng):
+    """scripts/lenard_bernstein_conservative.jl: DoubleMaxwellian(+-2), 41 knots, order 4, RK438."""
+    a, b, nknots, k = -10.0, 10.0, 41, 4
+    npart, dt, nsteps = 20000, 1e-2, 5
+    v = np.concatenate([rng.standard_normal(npart // 2) + 2.0, rng.standard_normal(npart - npart // 2) - 2.0])
+    w = np.full(npart, 1.0 / npart)
+    M = oracle.dirichlet_mass(a, b, nknots, k)
+    vs = vm.DeviceVSpline(ctx, a, b, nknots, k, 1)
+    p = vm.DeviceParticles(ctx, npart)
+    for cons in (True, False):
+        p.upload(np.zeros(npart), v, w)
+        diag = vs.rk438_run(p, dt, nsteps, 1.0, cons, 1)
+        vg = p.download(x=False, w=False)[1]
+        vo = v.copy()
+        for _ in range(nsteps):
+            oracle.lb_rk438_step(vo, w, dt, a, b, nknots, k, M, 1.0, cons)
+        assert np.max(np.abs(vg - vo)) <= 1e-11, cons
+        assert diag.shape == (nsteps + 1, 4)
+        assert np.allclose(diag[:, 0], dt * np.arange(nsteps + 1))
+        assert abs(diag[-1, 1] - vo.sum()) <= 1e-9 * npart and abs(diag[-1, 2] - (vo ** 2).sum()) <= 1e-9 * npart
+        if cons:     # momentum and energy drift as printed by the script (:64)
+            assert abs(diag[-1, 1] - diag[0, 1]) <= 1e-6 * npart
+            assert abs(diag[-1, 2] - diag[0, 2]) / diag[0, 2] <= 1e-6
+
+
+def test_mirror_lenard_bernstein(vm, oracle, ctx, rng):
+    vm.set_default_context(ctx)
+    npart = 1000
+    dist = vm.initialize_(vm.ParticleDistribution(1, 1, npart), vm.DoubleMaxwellian((-10.0, 10.0), 2.0), seed=11)
+    v0 = dist.particles.v[0].copy(); w0 = dist.particles.w[0].copy()
+    assert abs(v0[: npart // 2].mean() - 2) < 0.2 and abs(v0[npart // 2:].mean() + 2) < 0.2
+    sdist = vm.SplineDistribution(1, 1, 41, 4, (-10.0, 10.0), "Dirichlet")
+    model = vm.ConservativeLenardBernstein(dist, vm.CollisionEntropy(sdist))
+    integ = vm.GeometricIntegrator(model, (0.0, 0.05), 1e-2)
+    vm.run_(integ, None, diag_every=1)
+    M = oracle.dirichlet_mass(-10.0, 10.0, 41, 4)
+    vo = v0.copy()
+    for _ in range(5):
+        oracle.lb_rk438_step(vo, w0, 1e-2, -10.0, 10.0, 41, 4, M, 1.0, True)
+    assert np.max(np.abs(dist.particles.v[0] - vo)) <= 1e-11
+    assert integ.diagnostics.shape == (6, 4)
+    fs = vm.projection(None, dist, sdist)
+    assert abs(fs(0.0) - oracle.vspline_eval(np.array([0.0]), -10.0, 10.0, 41, 4, sdist.coefficients)[0][0]) < 1e-12
+    vm.set_default_context(None)
+
+
+# ----------------------------------------------------------------- loads -----
+def test_device_fills(vm, ctx):
+    n = 400000
+    p = vm.DeviceParticles(ctx, n)
+    p.fill(1, [0.03, 0.3, 0.1, 0.5, 4.5], 123)          # bump on tail
+    x, v, w = p.download()
+    L = 2 * math.pi / 0.3
+    assert x.min() >= 0 and x.max() < L and abs(w.sum() - L) < 1e-9
+    assert abs(np.mean(np.cos(0.3 * x)) - (-0.03 / 2)) < 5e-3            # density 1 - eps cos(kx)
+    assert abs((v > 3.0).mean() - 0.1) < 5e-3
+    p.fill(6, [0.05, 0.5], 5)                            # Landau
+    x, v, w = p.download()
+    assert abs(np.mean(np.cos(0.5 * x)) - 0.05 / 2) < 5e-3 and abs(v.std() - 1) < 5e-3
+    # sharding independence: two half shards == one full load
+    q = vm.DeviceParticles(ctx, n // 2)
+    q.fill(6, [0.05, 0.5], 5, 0, n)
+    xa = q.download()[0]
+    q.fill(6, [0.05, 0.5], 5, n // 2, n)
+    xb = q.download()[0]
+    assert np.array_equal(np.concatenate([xa, xb]), x)
+    p.fill(2, [-5.0, 5.0, 3.0], 9)
+    x, v, w = p.download()
+    assert abs(v[: n // 2].mean() - 3) < 1e-2 and abs(v[n // 2:].mean() + 3) < 1e-2 and abs(w.sum() - 1) < 1e-9
+
+
+def test_error_reporting(vm, ctx):
+    with pytest.raises(vm.VMError):
+        vm.DeviceField(ctx, 0.0, 1.0, 9, 16, 0)
+    with pytest.raises(vm.VMError):
+        vm.DeviceField(ctx, 1.0, 0.0, 4, 16, 0)
+    with pytest.raises(vm.VMError):
+        vm.DeviceField(ctx, 0.0, 1.0, 4, 2, 0)
+    with pytest.raises(vm.VMError):
+        vm.DeviceVSpline(ctx, 0.0, 1.0, 1, 4, 1)
+    with pytest.raises(vm.VMError):
+        vm.DeviceParticles(ctx, 4).fill(1, [0.1], 0)
+    c2 = vm.Context(0)
+    f = vm.DeviceField(c2, 0.0, 1.0, 4, 16, 0)
+    with pytest.raises(vm.VMError):
+        f.deposit(vm.DeviceParticles(ctx, 4), 0)       # different contexts

@@ -1,0 +1,454 @@
+// vm_ctx.cu -- context lifetime, error reporting, device scratch, NCCL plumbing,
+// and the particle container (device SoA replacing ParticleMethods.ParticleList).
+#include <dlfcn.h>
+
+#include <cstring>
+#include <mutex>
+
+#include "vm_internal.cuh"
+
+static thread_local std::string g_last_error;
+
+void vm_set_error(vm_ctx* ctx, const std::string& msg)
+{
+    g_last_error = msg;
+    if (ctx) ctx->last_error = msg;
+}
+
+void vm_use(vm_ctx* ctx) { VM_CUDA(cudaSetDevice(ctx->device)); }
+
+double* vm_partials(vm_ctx* ctx, size_t elems)
+{
+    if (elems > ctx->partials_elems) {
+        VM_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (ctx->partials) VM_CUDA(cudaFree(ctx->partials));
+        ctx->partials = nullptr;
+        ctx->partials_elems = 0;
+        size_t want = elems + elems / 2;
+        VM_CUDA(cudaMalloc(&ctx->partials, want * sizeof(double)));
+        ctx->partials_elems = want;
+    }
+    return ctx->partials;
+}
+
+double* vm_pinned(vm_ctx* ctx, size_t elems)
+{
+    if (elems > ctx->pinned_elems) {
+        VM_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (ctx->pinned) VM_CUDA(cudaFreeHost(ctx->pinned));
+        ctx->pinned = nullptr;
+        ctx->pinned_elems = 0;
+        size_t want = elems < 4096 ? 4096 : elems + elems / 2;
+        VM_CUDA(cudaMallocHost(&ctx->pinned, want * sizeof(double)));
+        ctx->pinned_elems = want;
+    }
+    return ctx->pinned;
+}
+
+void vm_launch_geometry(vm_ctx* ctx, int* grid, int* threads)
+{
+    int t = ctx->threads_per_cta > 0 ? ctx->threads_per_cta : 512;
+    int c = ctx->ctas_per_sm > 0 ? ctx->ctas_per_sm : 2;
+    *threads = t;
+    *grid = ctx->sm_count * c;
+}
+
+// ------------------------------------------------------------------ NCCL ----
+// libnccl.so.2 is resolved at run time (the copy bundled with PyTorch is already
+// mapped in a torchrun process; a Julia host would have NCCL_jll's).  Only the
+// handful of entry points the path needs are bound.
+namespace {
+struct NcclId { char internal[128]; };   // ncclUniqueId (nccl.h): 128 opaque bytes, passed by value
+struct NcclApi {
+    void* handle = nullptr;
+    int (*GetUniqueId)(void*) = nullptr;
+    int (*CommInitRank)(void**, int, NcclId, int) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+
+NcclApi g_nccl;
+std::mutex g_nccl_mu;
+
+NcclApi& nccl_api()
+{
+    std::lock_guard<std::mutex> lock(g_nccl_mu);
+    if (g_nccl.handle) return g_nccl;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    void* h = nullptr;
+    for (const char* nm : names) {
+        h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+        if (h) break;
+    }
+    if (!h) throw vm_error(VM_ERR_NCCL, std::string("cannot load libnccl.so.2: ") + dlerror());
+    g_nccl.GetUniqueId = (int (*)(void*))dlsym(h, "ncclGetUniqueId");
+    g_nccl.CommInitRank = (int (*)(void**, int, NcclId, int))dlsym(h, "ncclCommInitRank");
+    g_nccl.CommDestroy = (int (*)(void*))dlsym(h, "ncclCommDestroy");
+    g_nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(h, "ncclAllReduce");
+    g_nccl.GetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.CommDestroy || !g_nccl.AllReduce)
+        throw vm_error(VM_ERR_NCCL, "libnccl is missing required symbols");
+    g_nccl.handle = h;
+    return g_nccl;
+}
+
+void nccl_check(NcclApi& api, int rc, const char* what)
+{
+    if (rc != 0) {
+        std::string msg = std::string(what) + " failed: ";
+        msg += api.GetErrorString ? api.GetErrorString(rc) : "nccl error";
+        throw vm_error(VM_ERR_NCCL, msg);
+    }
+}
+}  // namespace
+
+void vm_allreduce_sum(vm_ctx* ctx, double* dev, size_t count)
+{
+    if (ctx->nranks <= 1) return;
+    NcclApi& api = nccl_api();
+    const int ncclDouble = 8, ncclSum = 0;   // ncclDataType_t / ncclRedOp_t values (nccl.h)
+    nccl_check(api, api.AllReduce(dev, dev, count, ncclDouble, ncclSum, ctx->nccl_comm, ctx->stream), "ncclAllReduce");
+}
+
+// ------------------------------------------------------------------- API ----
+extern "C" {
+
+int vm_abi_version(void) { return VM_ABI_VERSION; }
+
+const char* vm_last_error(vm_ctx* ctx) { return ctx ? ctx->last_error.c_str() : g_last_error.c_str(); }
+
+int vm_ctx_create(int device, vm_ctx** out)
+{
+    vm_ctx* ctx__ = nullptr;
+    try {
+        VM_REQUIRE(out != nullptr, "vm_ctx_create: out is NULL");
+        *out = nullptr;
+        int ndev = 0;
+        cudaError_t e = cudaGetDeviceCount(&ndev);
+        if (e != cudaSuccess || ndev == 0) {
+            (void)cudaGetLastError();
+            throw vm_error(VM_ERR_NO_DEVICE,
+                           "no CUDA device visible: libvlasov_b200 has no CPU path (sm_100a kernels only)");
+        }
+        VM_REQUIRE(device >= 0 && device < ndev, "vm_ctx_create: device ordinal out of range");
+        VM_CUDA(cudaSetDevice(device));
+        cudaDeviceProp prop;
+        VM_CUDA(cudaGetDeviceProperties(&prop, device));
+        if (prop.major < 10)
+            throw vm_error(VM_ERR_UNSUPPORTED, std::string("device ") + prop.name +
+                                                   " is not Blackwell (sm_100a code only)");
+        vm_ctx* c = new vm_ctx();
+        c->device = device;
+        c->sm_count = prop.multiProcessorCount;
+        c->cc_major = prop.major;
+        c->cc_minor = prop.minor;
+        c->smem_optin = prop.sharedMemPerBlockOptin;
+        VM_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        for (int i = 0; i < VM_MAX_EVENTS; ++i) VM_CUDA(cudaEventCreate(&c->events[i]));
+        *out = c;
+    }
+    catch (const vm_error& e) { vm_set_error(ctx__, e.what()); return e.code; }
+    catch (const std::exception& e) { vm_set_error(ctx__, e.what()); return VM_ERR_INVALID; }
+    return VM_OK;
+}
+
+int vm_ctx_destroy(vm_ctx* ctx)
+{
+    if (!ctx) return VM_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->nccl_comm) {
+        try { nccl_api().CommDestroy(ctx->nccl_comm); } catch (...) {}
+    }
+    for (int i = 0; i < VM_MAX_EVENTS; ++i) if (ctx->events[i]) cudaEventDestroy(ctx->events[i]);
+    if (ctx->partials) cudaFree(ctx->partials);
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return VM_OK;
+}
+
+int vm_sync(vm_ctx* ctx)
+{
+    VM_API_BEGIN(ctx)
+    VM_REQUIRE(ctx != nullptr, "vm_sync: ctx is NULL");
+    VM_CUDA(cudaStreamSynchronize(ctx->stream));
+    VM_API_END
+}
+
+int vm_ctx_device_info(vm_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor, size_t* free_bytes,
+                       size_t* total_bytes)
+{
+    VM_API_BEGIN(ctx)
+    VM_REQUIRE(ctx != nullptr, "vm_ctx_device_info: ctx is NULL");
+    if (sm_count) *sm_count = ctx->sm_count;
+    if (cc_major) *cc_major = ctx->cc_major;
+    if (cc_minor) *cc_minor = ctx->cc_minor;
+    size_t f = 0, t = 0;
+    VM_CUDA(cudaMemGetInfo(&f, &t));
+    if (free_bytes) *free_bytes = f;
+    if (total_bytes) *total_bytes = t;
+    VM_API_END
+}
+
+int vm_ctx_set_tuning(vm_ctx* ctx, const char* key, int value)
+{
+    VM_API_BEGIN(ctx)
+    VM_REQUIRE(ctx != nullptr && key != nullptr, "vm_ctx_set_tuning: NULL argument");
+    std::string k(key);
+    if (k == "ctas_per_sm") { VM_REQUIRE(value >= 0 && value <= 8, "ctas_per_sm out of range"); ctx->ctas_per_sm = value; }
+    else if (k == "threads_per_cta") {
+        VM_REQUIRE(value == 0 || (value >= 64 && value <= 1024 && value % 32 == 0), "threads_per_cta must be a multiple of 32 in 64..1024");
+        ctx->threads_per_cta = value;
+    }
+    else if (k == "replicas") {
+        VM_REQUIRE(value == 0 || (value >= 1 && value <= 32 && (value & (value - 1)) == 0), "replicas must be a power of two <= 32");
+        ctx->replicas = value;
+    }
+    else if (k == "use_graph") ctx->use_graph = value;
+    else throw vm_error(VM_ERR_INVALID, "unknown tuning key: " + k);
+    VM_API_END
+}
+
+int vm_comm_unique_id(void* out128)
+{
+    vm_ctx* ctx__ = nullptr;
+    try {
+        VM_REQUIRE(out128 != nullptr, "vm_comm_unique_id: out is NULL");
+        NcclApi& api = nccl_api();
+        nccl_check(api, api.GetUniqueId(out128), "ncclGetUniqueId");
+    }
+    catch (const vm_error& e) { vm_set_error(ctx__, e.what()); return e.code; }
+    return VM_OK;
+}
+
+int vm_ctx_comm_init(vm_ctx* ctx, int rank, int nranks, const void* id128)
+{
+    VM_API_BEGIN(ctx)
+    VM_REQUIRE(ctx != nullptr, "vm_ctx_comm_init: ctx is NULL");
+    VM_REQUIRE(nranks >= 1 && rank >= 0 && rank < nranks, "vm_ctx_comm_init: bad rank/nranks");
+    VM_REQUIRE(ctx->nccl_comm == nullptr, "vm_ctx_comm_init: communicator already initialised");
+    if (nranks > 1) {
+        VM_REQUIRE(id128 != nullptr, "vm_ctx_comm_init: id is NULL");
+        NcclApi& api = nccl_api();
+        NcclId id;
+        std::memcpy(id.internal, id128, 128);
+        nccl_check(api, api.CommInitRank(&ctx->nccl_comm, nranks, id, rank), "ncclCommInitRank");
+    }
+    ctx->rank = rank;
+    ctx->nranks = nranks;
+    VM_API_END
+}
+
+int vm_ctx_comm_info(vm_ctx* ctx, int* rank, int* nranks)
+{
+    VM_API_BEGIN(ctx)
+    VM_REQUIRE(ctx != nullptr, "vm_ctx_comm_info: ctx is NULL");
+    if (rank) *rank = ctx->rank;
+    if (nranks) *nranks = ctx->nranks;
+    VM_API_END
+}
+
+int vm_event_record(vm_ctx* ctx, int slot)
+{
+    VM_API_BEGIN(ctx)
+    VM_REQUIRE(ctx != nullptr && slot >= 0 && slot < VM_MAX_EVENTS, "vm_event_record: bad slot");
+    VM_CUDA(cudaEventRecord(ctx->events[slot], ctx->stream));
+    VM_API_END
+}
+
+int vm_event_elapsed_ms(vm_ctx* ctx, int a, int b, double* ms)
+{
+    VM_API_BEGIN(ctx)
+    VM_REQUIRE(ctx != nullptr && ms != nullptr && a >= 0 && a < VM_MAX_EVENTS && b >= 0 && b < VM_MAX_EVENTS,
+               "vm_event_elapsed_ms: bad argument");
+    VM_CUDA(cudaEventSynchronize(ctx->events[b]));
+    float f = 0.f;
+    VM_CUDA(cudaEventElapsedTime(&f, ctx->events[a], ctx->events[b]));
+    *ms = (double)f;
+    VM_API_END
+}
+
+unsigned long long vm_launch_count(vm_ctx* ctx) { return ctx ? ctx->launches : 0ull; }
+
+}  // extern "C"
+
+// -------------------------------------------------------------- particles ---
+namespace {
+
+// AoS (3 x N column-major: x,v,w interleaved) <-> SoA through shared memory so that
+// both the global reads and the global writes are coalesced.
+__global__ void __launch_bounds__(256) k_aos_to_soa(const double* __restrict__ z, double* __restrict__ x,
+                                                    double* __restrict__ v, double* __restrict__ w, long n)
+{
+    __shared__ double tile[3 * 256];
+    for (long base = (long)blockIdx.x * 256; base < n; base += (long)gridDim.x * 256) {
+        const long cnt = (n - base < 256) ? (n - base) : 256;
+        for (int i = threadIdx.x; i < 3 * cnt; i += 256) tile[i] = z[3 * base + i];
+        __syncthreads();
+        if (threadIdx.x < cnt) {
+            x[base + threadIdx.x] = tile[3 * threadIdx.x + 0];
+            v[base + threadIdx.x] = tile[3 * threadIdx.x + 1];
+            w[base + threadIdx.x] = tile[3 * threadIdx.x + 2];
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(256) k_soa_to_aos(const double* __restrict__ x, const double* __restrict__ v,
+                                                    const double* __restrict__ w, double* __restrict__ z, long n)
+{
+    __shared__ double tile[3 * 256];
+    for (long base = (long)blockIdx.x * 256; base < n; base += (long)gridDim.x * 256) {
+        const long cnt = (n - base < 256) ? (n - base) : 256;
+        if (threadIdx.x < cnt) {
+            tile[3 * threadIdx.x + 0] = x[base + threadIdx.x];
+            tile[3 * threadIdx.x + 1] = v[base + threadIdx.x];
+            tile[3 * threadIdx.x + 2] = w[base + threadIdx.x];
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < 3 * cnt; i += 256) z[3 * base + i] = tile[i];
+        __syncthreads();
+    }
+}
+
+// Host <-> device transfers of big arrays go through a pair of pinned bounce buffers so that
+// pageable host memory (a Julia Array) still streams at PCIe rate and overlaps with the copy engine.
+void copy_h2d(vm_ctx* ctx, double* dst, const double* src, size_t n)
+{
+    VM_CUDA(cudaMemcpyAsync(dst, src, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+}
+void copy_d2h(vm_ctx* ctx, double* dst, const double* src, size_t n)
+{
+    VM_CUDA(cudaMemcpyAsync(dst, src, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+}
+
+}  // namespace
+
+extern "C" {
+
+int vm_particles_create(vm_ctx* ctx, long n, vm_particles** out)
+{
+    VM_API_BEGIN(ctx)
+    VM_REQUIRE(ctx != nullptr && out != nullptr, "vm_particles_create: NULL argument");
+    VM_REQUIRE(n >= 0, "vm_particles_create: negative size");
+    *out = nullptr;
+    vm_particles* p = new vm_particles();
+    p->ctx = ctx;
+    p->n = n;
+    size_t bytes = (size_t)(n > 0 ? n : 1) * sizeof(double);
+    cudaError_t e1 = cudaMalloc(&p->x, bytes), e2 = cudaMalloc(&p->v, bytes), e3 = cudaMalloc(&p->w, bytes);
+    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) {
+        (void)cudaGetLastError();
+        if (p->x) cudaFree(p->x);
+        if (p->v) cudaFree(p->v);
+        if (p->w) cudaFree(p->w);
+        delete p;
+        throw vm_error(VM_ERR_NOMEM, "vm_particles_create: cudaMalloc failed");
+    }
+    VM_CUDA(cudaMemsetAsync(p->x, 0, bytes, ctx->stream));
+    VM_CUDA(cudaMemsetAsync(p->v, 0, bytes, ctx->stream));
+    VM_CUDA(cudaMemsetAsync(p->w, 0, bytes, ctx->stream));
+    *out = p;
+    VM_API_END
+}
+
+int vm_particles_destroy(vm_particles* p)
+{
+    if (!p) return VM_OK;
+    cudaSetDevice(p->ctx->device);
+    cudaStreamSynchronize(p->ctx->stream);
+    cudaFree(p->x); cudaFree(p->v); cudaFree(p->w);
+    if (p->a) cudaFree(p->a);
+    for (double* q : p->work) if (q) cudaFree(q);
+    delete p;
+    return VM_OK;
+}
+
+long vm_particles_size(vm_particles* p) { return p ? p->n : -1; }
+
+int vm_particles_upload_soa(vm_particles* p, const double* x, const double* v, const double* w)
+{
+    VM_API_BEGIN(p ? p->ctx : nullptr)
+    VM_REQUIRE(p != nullptr, "vm_particles_upload_soa: NULL handle");
+    if (p->n > 0) {
+        if (x) copy_h2d(p->ctx, p->x, x, (size_t)p->n);
+        if (v) copy_h2d(p->ctx, p->v, v, (size_t)p->n);
+        if (w) copy_h2d(p->ctx, p->w, w, (size_t)p->n);
+        VM_CUDA(cudaStreamSynchronize(p->ctx->stream));   // host buffers are only borrowed for the call
+    }
+    VM_API_END
+}
+
+int vm_particles_download_soa(vm_particles* p, double* x, double* v, double* w)
+{
+    VM_API_BEGIN(p ? p->ctx : nullptr)
+    VM_REQUIRE(p != nullptr, "vm_particles_download_soa: NULL handle");
+    if (p->n > 0) {
+        if (x) copy_d2h(p->ctx, x, p->x, (size_t)p->n);
+        if (v) copy_d2h(p->ctx, v, p->v, (size_t)p->n);
+        if (w) copy_d2h(p->ctx, w, p->w, (size_t)p->n);
+    }
+    VM_CUDA(cudaStreamSynchronize(p->ctx->stream));
+    VM_API_END
+}
+
+int vm_particles_upload_aos(vm_particles* p, const double* z)
+{
+    VM_API_BEGIN(p ? p->ctx : nullptr)
+    VM_REQUIRE(p != nullptr && z != nullptr, "vm_particles_upload_aos: NULL argument");
+    if (p->n > 0) {
+        vm_ctx* ctx = p->ctx;
+        // stage in chunks through the scratch buffer to bound the extra device memory
+        const long chunk = 1L << 22;   // particles per chunk (96 MiB of AoS)
+        double* stage = vm_partials(ctx, (size_t)3 * (size_t)(p->n < chunk ? p->n : chunk));
+        for (long off = 0; off < p->n; off += chunk) {
+            long cnt = p->n - off < chunk ? p->n - off : chunk;
+            copy_h2d(ctx, stage, z + 3 * off, (size_t)3 * cnt);
+            int grid = (int)((cnt + 255) / 256);
+            if (grid > ctx->sm_count * 8) grid = ctx->sm_count * 8;
+            k_aos_to_soa<<<grid, 256, 0, ctx->stream>>>(stage, p->x + off, p->v + off, p->w + off, cnt);
+            VM_LAUNCHED(ctx);
+        }
+        VM_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    VM_API_END
+}
+
+int vm_particles_download_aos(vm_particles* p, double* z)
+{
+    VM_API_BEGIN(p ? p->ctx : nullptr)
+    VM_REQUIRE(p != nullptr && z != nullptr, "vm_particles_download_aos: NULL argument");
+    if (p->n > 0) {
+        vm_ctx* ctx = p->ctx;
+        const long chunk = 1L << 22;
+        double* stage = vm_partials(ctx, (size_t)3 * (size_t)(p->n < chunk ? p->n : chunk));
+        for (long off = 0; off < p->n; off += chunk) {
+            long cnt = p->n - off < chunk ? p->n - off : chunk;
+            int grid = (int)((cnt + 255) / 256);
+            if (grid > ctx->sm_count * 8) grid = ctx->sm_count * 8;
+            k_soa_to_aos<<<grid, 256, 0, ctx->stream>>>(p->x + off, p->v + off, p->w + off, stage, cnt);
+            VM_LAUNCHED(ctx);
+            copy_d2h(ctx, z + 3 * off, stage, (size_t)3 * cnt);
+        }
+    }
+    VM_CUDA(cudaStreamSynchronize(p->ctx->stream));
+    VM_API_END
+}
+
+int vm_particles_copy(vm_particles* dst, vm_particles* src)
+{
+    VM_API_BEGIN(dst ? dst->ctx : nullptr)
+    VM_REQUIRE(dst != nullptr && src != nullptr, "vm_particles_copy: NULL handle");
+    VM_REQUIRE(dst->ctx == src->ctx && dst->n == src->n, "vm_particles_copy: handles differ in context or size");
+    size_t bytes = (size_t)dst->n * sizeof(double);
+    if (bytes) {
+        VM_CUDA(cudaMemcpyAsync(dst->x, src->x, bytes, cudaMemcpyDeviceToDevice, dst->ctx->stream));
+        VM_CUDA(cudaMemcpyAsync(dst->v, src->v, bytes, cudaMemcpyDeviceToDevice, dst->ctx->stream));
+        VM_CUDA(cudaMemcpyAsync(dst->w, src->w, bytes, cudaMemcpyDeviceToDevice, dst->ctx->stream));
+    }
+    VM_API_END
+}
+
+}  // extern "C"

@@ -1,0 +1,162 @@
+// vm_deposit.cuh -- shared-memory replica-grid deposition machinery used by the x-space
+// (vm_push.cu) and v-space (vm_vspline.cu) particle passes.
+//
+// Deposition never uses shared-memory atomics on the hot variants (fp64 shared atomics are CAS
+// loops): every warp owns private replica grids in shared memory and resolves intra-warp
+// collisions by grouping lanes by cell (__match_any_sync) and reducing each group in lane order,
+// so the result is bit-reproducible for a fixed launch geometry.
+#pragma once
+#include "vm_internal.cuh"
+
+enum { VAR_PRIV = 0, VAR_MATCH = 1, VAR_ATOMIC = 2 };
+
+// ---------------------------------------------------------------- scatter ---
+// Add val[j] to basis index (b0 + j) mod n, j < K, in this warp's replica grid.
+template <int K, int VAR>
+__device__ __forceinline__ void scatter(double* __restrict__ wg, int n, int rep_log2, int rep, int lane,
+                                        int b0, const double (&val)[K], bool active)
+{
+    if (VAR == VAR_PRIV) {
+        if (active) {
+#pragma unroll
+            for (int j = 0; j < K; ++j) {
+                double* a = wg + (wrap_add(b0, j, n) << 5) + lane;
+                *a += val[j];
+            }
+        }
+        return;
+    }
+    // group the lanes that target the same (cell, replica): in-warp sort-by-cell
+    const unsigned key = active ? (((unsigned)b0 << 5) | (unsigned)rep) : (0x80000000u | (unsigned)lane);
+    const unsigned peers = __match_any_sync(VM_FULL_MASK, key);
+    const int leader = __ffs(peers) - 1;
+    const bool is_leader = (lane == leader);
+    double acc[K];
+#pragma unroll
+    for (int j = 0; j < K; ++j) acc[j] = val[j];
+    // segmented reduce in increasing lane order (fixed order => bit-reproducible)
+    unsigned todo = is_leader ? (peers & ~(1u << lane)) : 0u;
+    while (__any_sync(VM_FULL_MASK, todo != 0u)) {
+        const int src = todo ? (__ffs(todo) - 1) : lane;
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            const double t = __shfl_sync(VM_FULL_MASK, val[j], src);
+            if (todo) acc[j] += t;
+        }
+        todo &= todo - 1u;
+    }
+    if (VAR == VAR_MATCH) {
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            if (is_leader && active) {
+                double* a = wg + (wrap_add(b0, j, n) << rep_log2) + rep;
+                *a += acc[j];
+            }
+            __syncwarp();
+        }
+    } else {  // VAR_ATOMIC: one warp-aggregated shared atomic per distinct cell
+        if (is_leader && active) {
+#pragma unroll
+            for (int j = 0; j < K; ++j) atomicAdd(wg + (wrap_add(b0, j, n) << rep_log2) + rep, acc[j]);
+        }
+    }
+}
+
+// Sum all replica copies of every basis index in a fixed order and emit the CTA's partial row.
+template <int VAR>
+__device__ __forceinline__ void flush_grid(const double* __restrict__ grid, double* __restrict__ scratch,
+                                           double* __restrict__ out, int n, int rep_log2, int nwarps, int ncols)
+{
+    const int T = blockDim.x;
+    const int gsz = n << rep_log2;
+    const int ncopies = (VAR == VAR_ATOMIC) ? (1 << rep_log2) : (nwarps << rep_log2);
+    const int R = 1 << rep_log2;
+    __syncthreads();
+    int P = 1;
+    while (2 * P * n <= T && 2 * P <= ncopies) P *= 2;   // P partial sums per index
+    for (int base = 0; base < n; base += T) {           // (only one trip when n <= T)
+        const int t = threadIdx.x;
+        if (P > 1) {
+            if (t < n * P) {
+                const int i = t % n, part = t / n;
+                double s = 0.0;
+                for (int c = part; c < ncopies; c += P) {
+                    const int wq = c >> rep_log2, r = c & (R - 1);
+                    s += grid[(VAR == VAR_ATOMIC ? 0 : wq * gsz) + (i << rep_log2) + r];
+                }
+                scratch[part * n + i] = s;
+            }
+            __syncthreads();
+            if (t < n) {
+                double s = 0.0;
+                for (int part = 0; part < P; ++part) s += scratch[part * n + t];
+                if (VAR == VAR_ATOMIC) atomicAdd(out + t, s);
+                else out[(size_t)blockIdx.x * ncols + t] = s;
+            }
+        } else {
+            const int i = base + t;
+            if (i < n) {
+                double s = 0.0;
+                for (int c = 0; c < ncopies; ++c) {
+                    const int wq = c >> rep_log2, r = c & (R - 1);
+                    s += grid[(VAR == VAR_ATOMIC ? 0 : wq * gsz) + (i << rep_log2) + r];
+                }
+                if (VAR == VAR_ATOMIC) atomicAdd(out + i, s);
+                else out[(size_t)blockIdx.x * ncols + i] = s;
+            }
+        }
+    }
+    if (VAR != VAR_ATOMIC && threadIdx.x < ncols - n) out[(size_t)blockIdx.x * ncols + n + threadIdx.x] = 0.0;
+}
+
+
+// ================================================================ host ======
+struct DepositPlan {
+    int var, rep_log2, grid, threads;
+    size_t smem;
+};
+
+// Choose CTA shape + replica count so that the replica grids fit in shared memory.
+inline DepositPlan plan_deposit(vm_ctx* ctx, int n, bool with_dcoef, int mode)
+{
+    const int sm = ctx->sm_count;
+    struct Try { int ctas, threads; };
+    std::vector<Try> tries;
+    if (ctx->ctas_per_sm > 0 || ctx->threads_per_cta > 0) {
+        tries.push_back({ctx->ctas_per_sm > 0 ? ctx->ctas_per_sm : 2, ctx->threads_per_cta > 0 ? ctx->threads_per_cta : 512});
+    } else {
+        tries = {{2, 512}, {1, 512}, {1, 256}, {1, 128}, {1, 64}};
+    }
+    const size_t sm_total = 227 * 1024;   // usable shared memory per SM on sm_100
+    for (const Try& t : tries) {
+        const int nwarps = t.threads / 32;
+        size_t budget = sm_total / t.ctas - 1024;            // 1 KB per-CTA system reservation
+        if (budget > ctx->smem_optin) budget = ctx->smem_optin;
+        const size_t fixed = ((with_dcoef ? (size_t)n : 0) + (size_t)t.threads) * sizeof(double);
+        if (budget <= fixed) continue;
+        const size_t avail = (budget - fixed) / sizeof(double);
+        DepositPlan pl{};
+        pl.grid = sm * t.ctas;
+        pl.threads = t.threads;
+        if (mode == VM_DEPOSIT_ATOMIC) {
+            int rl = 5;
+            while (rl > 0 && ((size_t)n << rl) > avail) --rl;
+            if (((size_t)n << rl) > avail) continue;
+            pl.var = VAR_ATOMIC;
+            pl.rep_log2 = rl;
+            pl.smem = fixed + ((size_t)n << rl) * sizeof(double);
+            return pl;
+        }
+        const size_t per_warp = avail / nwarps;
+        int rl = 5;
+        if (ctx->replicas > 0) { rl = 0; while ((1 << rl) < ctx->replicas) ++rl; }
+        while (rl > 0 && ((size_t)n << rl) > per_warp && ctx->replicas == 0) --rl;
+        if (((size_t)n << rl) > per_warp) continue;
+        pl.var = (rl == 5) ? VAR_PRIV : VAR_MATCH;
+        pl.rep_log2 = rl;
+        pl.smem = fixed + ((size_t)n << rl) * nwarps * sizeof(double);
+        return pl;
+    }
+    throw vm_error(VM_ERR_UNSUPPORTED, "deposit: replica grids do not fit in shared memory for this n_basis/tuning");
+}
+

@@ -1,0 +1,211 @@
+// vm_internal.cuh -- shared host/device internals of libvlasov_b200.so (sm_100a, fp64).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "vlasov_b200.h"
+
+#define VM_MIN_ORDER 2
+#define VM_MAX_ORDER 6
+#define VM_MAX_NBASIS 4096
+#define VM_FULL_MASK 0xffffffffu
+#define VM_DIAG_COLS 4          // extra columns appended to a partial row: [sum w v^2, sum w v, sum w, spare]
+#define VM_MAX_EVENTS 16
+
+struct vm_error : public std::runtime_error {
+    int code;
+    vm_error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+#define VM_CUDA(expr)                                                                         \
+    do {                                                                                      \
+        cudaError_t e__ = (expr);                                                             \
+        if (e__ != cudaSuccess)                                                               \
+            throw vm_error(VM_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__)); \
+    } while (0)
+
+#define VM_REQUIRE(cond, msg)                                   \
+    do {                                                        \
+        if (!(cond)) throw vm_error(VM_ERR_INVALID, (msg));     \
+    } while (0)
+
+struct vm_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int sm_count = 0, cc_major = 0, cc_minor = 0;
+    size_t smem_optin = 0;
+    std::string last_error;
+    unsigned long long launches = 0;
+    cudaEvent_t events[VM_MAX_EVENTS] = {};
+    // tuning (0 = auto)
+    int ctas_per_sm = 0, threads_per_cta = 0, replicas = 0, use_graph = 0;
+    // communicator (one process per GPU)
+    void* nccl_comm = nullptr;
+    int rank = 0, nranks = 1;
+    // scratch: per-CTA partial rows for the fixed-order reductions
+    double* partials = nullptr;
+    size_t partials_elems = 0;
+    // pinned host staging for small read-backs
+    double* pinned = nullptr;
+    size_t pinned_elems = 0;
+};
+
+struct vm_particles {
+    vm_ctx* ctx = nullptr;
+    long n = 0;
+    double *x = nullptr, *v = nullptr, *w = nullptr;
+    double* a = nullptr;        // lazily allocated per-particle work array (E / vdot)
+    double* work[5] = {};       // lazily allocated RK stage arrays
+};
+
+// Map a position to (first basis index, xi) on a uniform periodic grid.
+struct CellMap {
+    double inv_h;     // n / (b - a)
+    double off;       // -a * inv_h
+    int n;            // number of cells == number of periodic basis functions
+    int bias;         // multiple of n plus index shift; makes the raw cell index positive
+    unsigned inv_n;   // floor(2^32 / n), for the fast modulo
+};
+
+struct vm_field {
+    vm_ctx* ctx = nullptr;
+    double a = 0, b = 0, h = 0;
+    int order = 0, n = 0, shift = 0;
+    CellMap map{};
+    double *rhs = nullptr, *phi = nullptr, *dcoef = nullptr;  // device, n each
+    double *G = nullptr, *GD = nullptr;                       // device: circulant pseudo-inverse kernels
+    double *stencil_s = nullptr;                              // device: stiffness stencil, 2k-1 entries
+    double *diag = nullptr;                                   // device: [W, K, M, sum_w] rows
+    int diag_rows = 0;
+    double mass_st[VM_MAX_ORDER] = {}, stiff_st[VM_MAX_ORDER] = {};
+};
+
+struct vm_vspline {
+    vm_ctx* ctx = nullptr;
+    double a = 0, b = 0, h = 0;
+    int order = 0, nknots = 0, ncell = 0, npar = 0, nv = 0, bc = 1;
+    std::vector<double> mass;          // host nv x nv
+    double *rhs = nullptr;             // device npar (parent indexing)
+    double *coef = nullptr;            // device npar (parent indexing, zeros at dropped ends)
+    double *minv = nullptr;            // device nv x nv dense inverse of the mass matrix
+    double *cellpoly = nullptr;        // device ncell x k x k: A[c][j][m], B_{c+j} = sum_m A xi^m
+    double *poly = nullptr;            // device ncell x k: f_s on cell c = sum_m poly[c][m] xi^m
+    double *moments = nullptr;         // device 8: [5 sums, A1, A2, spare]
+    double *diag = nullptr;            // device rows [t, sum v, sum v^2, spare]
+    int diag_rows = 0;
+};
+
+void vm_set_error(vm_ctx* ctx, const std::string& msg);
+void vm_use(vm_ctx* ctx);                         // cudaSetDevice
+double* vm_partials(vm_ctx* ctx, size_t elems);   // grow-only device scratch
+double* vm_pinned(vm_ctx* ctx, size_t elems);     // grow-only pinned host scratch
+void vm_allreduce_sum(vm_ctx* ctx, double* dev, size_t count);  // no-op when nranks == 1
+void vm_launch_geometry(vm_ctx* ctx, int* grid, int* threads);
+
+#define VM_API_BEGIN(ctxexpr)          \
+    vm_ctx* ctx__ = (ctxexpr);         \
+    try {                              \
+        if (ctx__) vm_use(ctx__);
+
+#define VM_API_END                                        \
+    }                                                     \
+    catch (const vm_error& e) {                           \
+        vm_set_error(ctx__, e.what());                    \
+        return e.code;                                    \
+    }                                                     \
+    catch (const std::bad_alloc&) {                       \
+        vm_set_error(ctx__, "host allocation failed");    \
+        return VM_ERR_NOMEM;                              \
+    }                                                     \
+    catch (const std::exception& e) {                     \
+        vm_set_error(ctx__, e.what());                    \
+        return VM_ERR_INVALID;                            \
+    }                                                     \
+    return VM_OK;
+
+#define VM_LAUNCHED(ctx)                       \
+    do {                                       \
+        ++(ctx)->launches;                     \
+        VM_CUDA(cudaGetLastError());           \
+    } while (0)
+
+// ------------------------------------------------------------------ device --
+#ifdef __CUDACC__
+
+// K nonzero uniform B-splines of order K at local coordinate xi in [0,1), increasing index.
+// de Boor recursion specialised to unit knot spacing (all denominators are the integers 1..K-1).
+template <int K>
+__device__ __forceinline__ void bspline_uniform(double xi, double (&N)[K])
+{
+    N[0] = 1.0;
+#pragma unroll
+    for (int j = 1; j < K; ++j) {
+        const double inv = 1.0 / (double)j;
+        double saved = 0.0;
+#pragma unroll
+        for (int r = 0; r < j; ++r) {
+            const double temp = N[r] * inv;
+            const double right = (double)(r + 1) - xi;
+            const double left = xi + (double)(j - r - 1);
+            N[r] = fma(right, temp, saved);
+            saved = left * temp;
+        }
+        N[j] = saved;
+    }
+}
+
+__device__ __forceinline__ void cell_of(const CellMap& m, double x, int& base, double& xi)
+{
+    const double t = fma(x, m.inv_h, m.off);
+    const double fl = floor(t);
+    xi = t - fl;
+    const unsigned u = (unsigned)(__double2int_rd(t) + m.bias);   // in [0, 2^31)
+    const unsigned q = __umulhi(u, m.inv_n);
+    unsigned r = u - q * (unsigned)m.n;
+    if (r >= (unsigned)m.n) r -= (unsigned)m.n;
+    base = (int)r;
+}
+
+__device__ __forceinline__ int wrap_add(int i, int j, int n)
+{
+    int r = i + j;
+    return r >= n ? r - n : r;
+}
+
+// streaming 16-byte loads/stores (read once / written once per pass)
+__device__ __forceinline__ double2 ld_stream2(const double* p)
+{
+    double2 r;
+    asm volatile("ld.global.cs.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void st_stream2(double* p, double2 v)
+{
+    asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
+}
+__device__ __forceinline__ double ld_stream(const double* p)
+{
+    double r;
+    asm volatile("ld.global.cs.f64 %0, [%1];" : "=d"(r) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void st_stream(double* p, double v)
+{
+    asm volatile("st.global.cs.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+
+// fixed-order warp tree sum (xor butterfly: every lane ends with the same bits)
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(VM_FULL_MASK, v, o);
+    return v;
+}
+
+#endif  // __CUDACC__

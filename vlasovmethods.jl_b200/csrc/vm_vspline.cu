@@ -1,0 +1,663 @@
+// vm_vspline.cu -- velocity-space spline projection and the Lenard-Bernstein right-hand sides.
+//
+// Replaces (reference paths):
+//   SplineDistribution(1,1,nknots,order,domain,:Dirichlet)   src/distributions/spline_distribution.jl:1-36
+//   projection(v, dist, sdist)                               src/projections/distribution.jl:35-55
+//   compute_f_densities / compute_df_densities               src/projections/density.jl:6-52
+//   compute_coefficients, CLB_rhs!, CLB_rhs_GI!              src/models/lenard_bernstein_conservative.jl:11-50
+//   LB_rhs!, LB_rhs_GI!                                      src/models/lenard_bernstein.jl:20-34
+//   run!(::GeometricIntegrator) with RK438                   src/methods/geometric_integrator.jl:12-44
+//
+// Data layout: the clamped basis is kept in PARENT indexing (npar = nknots + order - 2 functions;
+// the Dirichlet recombination just drops parent 0 and npar-1).  Every cell c carries the exact
+// polynomial pieces A[c][j][m] of its `order` nonzero B-splines (general knots at the clamped
+// ends, uniform in the interior), so evaluation of f_s and f_s' at a particle is one Horner sweep
+// over poly[c][0..order) -- no knot search, no boundary special cases.
+#include <cstring>
+
+#include "vm_deposit.cuh"
+#include "vm_internal.cuh"
+#include "vm_spline_host.hpp"
+
+struct VCell {
+    double inv_h, off;   // t = v * inv_h + off  in cell units
+    int ncell, k;
+};
+
+__device__ __forceinline__ bool vcell_of(const VCell& m, double v, int& c, double& xi)
+{
+    const double t = fma(v, m.inv_h, m.off);
+    if (!(t >= 0.0 && t <= (double)m.ncell)) return false;   // outside [vmin, vmax] (or NaN): no contribution
+    c = min(__double2int_rd(t), m.ncell - 1);
+    xi = t - (double)c;
+    return true;
+}
+
+// ------------------------------------------------------------ v deposit -----
+template <int K, int VAR>
+__device__ __forceinline__ void vdeposit_one(double vp, double wp, bool active, const VCell& m,
+                                             const double* __restrict__ cellpoly, double* __restrict__ wg,
+                                             int npar, int rep_log2, int rep, int lane)
+{
+    int c = 0;
+    double xi = 0.0;
+    active = active && vcell_of(m, vp, c, xi);
+    double val[K];
+    if (c >= K - 1 && c <= m.ncell - K) {
+        bspline_uniform<K>(xi, val);                      // interior cell: uniform cardinal splines
+    } else {
+        const double* A = cellpoly + (size_t)c * K * K;   // clamped end: exact polynomial pieces
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            double s = __ldg(A + j * K + K - 1);
+#pragma unroll
+            for (int q = K - 2; q >= 0; --q) s = fma(s, xi, __ldg(A + j * K + q));
+            val[j] = s;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < K; ++j) val[j] *= wp;
+    scatter<K, VAR>(wg, npar, rep_log2, rep, lane, c, val, active);
+}
+
+template <int K, int VAR>
+__global__ void __launch_bounds__(1024, 1)
+k_v_deposit(const double* __restrict__ v, const double* __restrict__ w, long np, VCell m,
+            const double* __restrict__ cellpoly, int npar, int rep_log2, double* __restrict__ out)
+{
+    extern __shared__ double smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int gsz = npar << rep_log2;
+    const int gtotal = (VAR == VAR_ATOMIC) ? gsz : gsz * nwarps;
+    double* grid = smem;
+    double* scratch = grid + gtotal;
+    for (int i = threadIdx.x; i < gtotal; i += blockDim.x) grid[i] = 0.0;
+    __syncthreads();
+    double* wg = (VAR == VAR_ATOMIC) ? grid : grid + warp * gsz;
+    const int rep = ((VAR == VAR_ATOMIC) ? warp : lane) & ((1 << rep_log2) - 1);
+
+    const long npairs = np >> 1;
+    const long stride = (long)gridDim.x * blockDim.x;
+    const long gtid = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long iters = (npairs + stride - 1) / stride;
+    double2 cv = make_double2(0., 0.), cw = cv, nv = cv, nw = cv;
+    if (gtid < npairs) { cv = ld_stream2(v + 2 * gtid); cw = ld_stream2(w + 2 * gtid); }
+    for (long it = 0; it < iters; ++it) {
+        const long q = it * stride + gtid, qn = q + stride;
+        const bool active = q < npairs;
+        if (qn < npairs) { nv = ld_stream2(v + 2 * qn); nw = ld_stream2(w + 2 * qn); }
+        vdeposit_one<K, VAR>(cv.x, cw.x, active, m, cellpoly, wg, npar, rep_log2, rep, lane);
+        vdeposit_one<K, VAR>(cv.y, cw.y, active, m, cellpoly, wg, npar, rep_log2, rep, lane);
+        cv = nv; cw = nw;
+    }
+    if ((np & 1) && blockIdx.x == 0 && warp == 0) {
+        const bool active = (lane == 0);
+        vdeposit_one<K, VAR>(active ? v[np - 1] : 0.0, active ? w[np - 1] : 0.0, active, m, cellpoly, wg, npar,
+                             rep_log2, rep, lane);
+    }
+    flush_grid<VAR>(grid, scratch, out, npar, rep_log2, nwarps, npar);
+}
+
+// ------------------------------------------------------------- small solves -
+// coef_par[off + i] = sum_j Minv[i][j] rhs_par[off + j]: one warp per row, fixed-order tree.
+__global__ void __launch_bounds__(256) k_v_solve(const double* __restrict__ minv, const double* __restrict__ rhs_par,
+                                                 int nv, int off, int npar, double* __restrict__ coef_par)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int i = blockIdx.x * 8 + warp;
+    if (i < nv) {
+        double s = 0.0;
+        for (int j = lane; j < nv; j += 32) s = fma(minv[(size_t)i * nv + j], rhs_par[off + j], s);
+        s = warp_sum(s);
+        if (lane == 0) coef_par[off + i] = s;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0 && off == 1) { coef_par[0] = 0.0; coef_par[npar - 1] = 0.0; }
+}
+
+// poly[c][m] = sum_j coef_par[c + j] * A[c][j][m]
+__global__ void k_v_poly(const double* __restrict__ coef_par, const double* __restrict__ cellpoly, int ncell, int k,
+                         double* __restrict__ poly)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < ncell * k) {
+        const int c = t / k, m = t % k;
+        double s = 0.0;
+        for (int j = 0; j < k; ++j) s = fma(coef_par[c + j], cellpoly[((size_t)c * k + j) * k + m], s);
+        poly[t] = s;
+    }
+}
+
+template <int K>
+__device__ __forceinline__ void eval_f_df(const double* __restrict__ psh, const VCell& m, double v, double& f, double& df)
+{
+    int c;
+    double xi;
+    f = 0.0;
+    df = 0.0;
+    if (!vcell_of(m, v, c, xi)) return;
+    const double* q = psh + c * K;
+    double sf = q[K - 1], sd = (double)(K - 1) * q[K - 1];
+#pragma unroll
+    for (int j = K - 2; j >= 0; --j) {
+        sf = fma(sf, xi, q[j]);
+        if (j >= 1) sd = fma(sd, xi, (double)j * q[j]);
+    }
+    f = sf;
+    df = (K > 1) ? sd * m.inv_h : 0.0;
+}
+
+// five unweighted particle sums: [sum f, sum v f, sum v^2 f, sum f', sum v f']
+template <int K>
+__global__ void __launch_bounds__(512, 2)
+k_v_moments(const double* __restrict__ v, long np, VCell m, const double* __restrict__ poly, double* __restrict__ out)
+{
+    extern __shared__ double psh[];
+    for (int i = threadIdx.x; i < m.ncell * K; i += blockDim.x) psh[i] = poly[i];
+    __syncthreads();
+    double s[5] = {0., 0., 0., 0., 0.};
+    const long stride = (long)gridDim.x * blockDim.x;
+    for (long p = (long)blockIdx.x * blockDim.x + threadIdx.x; p < np; p += stride) {
+        const double vp = ld_stream(v + p);
+        double f, df;
+        eval_f_df<K>(psh, m, vp, f, df);
+        s[0] += f;
+        s[1] = fma(vp, f, s[1]);
+        s[2] = fma(vp * vp, f, s[2]);
+        s[3] += df;
+        s[4] = fma(vp, df, s[4]);
+    }
+    __shared__ double red[5][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+#pragma unroll
+    for (int q = 0; q < 5; ++q) {
+        const double t = warp_sum(s[q]);
+        if (lane == 0) red[q][warp] = t;
+    }
+    __syncthreads();
+    if (threadIdx.x < 8) {
+        double t = 0.0;
+        if (threadIdx.x < 5)
+            for (int q = 0; q < nwarps; ++q) t += red[threadIdx.x][q];
+        out[(size_t)blockIdx.x * 8 + threadIdx.x] = t;
+    }
+}
+
+// A1, A2 of compute_coefficients (lenard_bernstein_conservative.jl:13-18) from the five sums
+__global__ void k_clb_coeffs(double* __restrict__ mom, int conservative)
+{
+    if (threadIdx.x == 0) {
+        if (conservative) {
+            const double n = mom[0], nu = mom[1], ne = mom[2];
+            const double B1 = -mom[3], B2 = -mom[4];
+            const double den = n * ne - nu * nu;
+            mom[5] = (ne * B1 - nu * B2) / den;
+            mom[6] = -(nu * B1 - n * B2) / den;
+        } else {
+            mom[5] = 0.0;   // LB: vdot = -nu (f' + v f)
+            mom[6] = 1.0;
+        }
+    }
+}
+
+// vdot_p = -nu (f'(v_p) + (A1 + A2 v_p) f(v_p))
+template <int K>
+__global__ void __launch_bounds__(512, 2)
+k_v_rhs(const double* __restrict__ v, long np, VCell m, const double* __restrict__ poly,
+        const double* __restrict__ mom, double nu, double* __restrict__ vdot)
+{
+    extern __shared__ double psh[];
+    for (int i = threadIdx.x; i < m.ncell * K; i += blockDim.x) psh[i] = poly[i];
+    __syncthreads();
+    const double A1 = mom[5], A2 = mom[6];
+    const long stride = (long)gridDim.x * blockDim.x;
+    for (long p = (long)blockIdx.x * blockDim.x + threadIdx.x; p < np; p += stride) {
+        const double vp = ld_stream(v + p);
+        double f, df;
+        eval_f_df<K>(psh, m, vp, f, df);
+        st_stream(vdot + p, -nu * (df + fma(A2, vp, A1) * f));
+    }
+}
+
+// f_s and f_s' at arbitrary points (plotting / tests)
+template <int K>
+__global__ void k_v_eval(const double* __restrict__ v, long np, VCell m, const double* __restrict__ poly,
+                         double* __restrict__ f, double* __restrict__ df)
+{
+    extern __shared__ double psh[];
+    for (int i = threadIdx.x; i < m.ncell * K; i += blockDim.x) psh[i] = poly[i];
+    __syncthreads();
+    const long stride = (long)gridDim.x * blockDim.x;
+    for (long p = (long)blockIdx.x * blockDim.x + threadIdx.x; p < np; p += stride) {
+        double a, b;
+        eval_f_df<K>(psh, m, v[p], a, b);
+        f[p] = a;
+        df[p] = b;
+    }
+}
+
+// q = v + dt (a1 k1 + a2 k2 + a3 k3 + a4 k4)   (RK stage assembly / final update; null k's skipped)
+__global__ void __launch_bounds__(512, 2)
+k_rk_combine(const double* v, const double* __restrict__ k1, const double* __restrict__ k2,
+             const double* __restrict__ k3, const double* __restrict__ k4, double a1, double a2, double a3, double a4,
+             double dt, long np, double* q /* may alias v (final update) */)
+{
+    const long stride = (long)gridDim.x * blockDim.x;
+    for (long p = (long)blockIdx.x * blockDim.x + threadIdx.x; p < np; p += stride) {
+        double s = a1 * ld_stream(k1 + p);
+        if (k2) s = fma(a2, ld_stream(k2 + p), s);
+        if (k3) s = fma(a3, ld_stream(k3 + p), s);
+        if (k4) s = fma(a4, ld_stream(k4 + p), s);
+        st_stream(q + p, fma(dt, s, v[p]));
+    }
+}
+
+// [sum v, sum v^2] (script diagnostics, lenard_bernstein_conservative.jl:49-50)
+__global__ void __launch_bounds__(512, 2) k_v_sums(const double* __restrict__ v, long np, double* __restrict__ out)
+{
+    double s1 = 0.0, s2 = 0.0;
+    const long stride = (long)gridDim.x * blockDim.x;
+    for (long p = (long)blockIdx.x * blockDim.x + threadIdx.x; p < np; p += stride) {
+        const double vp = ld_stream(v + p);
+        s1 += vp;
+        s2 = fma(vp, vp, s2);
+    }
+    __shared__ double red[2][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    s1 = warp_sum(s1); s2 = warp_sum(s2);
+    if (lane == 0) { red[0][warp] = s1; red[1][warp] = s2; }
+    __syncthreads();
+    if (threadIdx.x < 8) {
+        double t = 0.0;
+        if (threadIdx.x < 2)
+            for (int q = 0; q < nwarps; ++q) t += red[threadIdx.x][q];
+        out[(size_t)blockIdx.x * 8 + threadIdx.x] = t;
+    }
+}
+
+__global__ void k_v_store_diag(double* __restrict__ row, double t, const double* __restrict__ sums)
+{
+    if (threadIdx.x == 0) { row[0] = t; row[1] = sums[0]; row[2] = sums[1]; row[3] = 0.0; }
+}
+
+__global__ void __launch_bounds__(256) k_reduce_rows8(const double* __restrict__ rows, int nrows, double* __restrict__ out)
+{
+    // out[c] = sum_r rows[r][c], c < 8: 32 chunks of rows, then the chunks in order
+    __shared__ double red[32][8];
+    const int c = threadIdx.x & 7, ch = threadIdx.x >> 3;
+    const int len = (nrows + 31) / 32;
+    double s = 0.0;
+    for (int r = ch * len; r < min(nrows, (ch + 1) * len); ++r) s += rows[(size_t)r * 8 + c];
+    red[ch][c] = s;
+    __syncthreads();
+    if (threadIdx.x < 8) {
+        double t = 0.0;
+        for (int q = 0; q < 32; ++q) t += red[q][threadIdx.x];
+        out[threadIdx.x] = t;
+    }
+}
+
+// ================================================================ host ======
+void vm_reduce_rows(vm_ctx* ctx, const double* rows, int nrows, int ncols, double* out);   // vm_field.cu
+
+namespace {
+
+VCell vcell(const vm_vspline* s)
+{
+    VCell m;
+    m.inv_h = (double)((long double)s->ncell / ((long double)s->b - (long double)s->a));
+    m.off = -s->a * m.inv_h;
+    m.ncell = s->ncell;
+    m.k = s->order;
+    return m;
+}
+
+void geometry(vm_ctx* ctx, int* grid, int* threads)
+{
+    vm_launch_geometry(ctx, grid, threads);
+    if (*threads > 512) *threads = 512;
+}
+
+template <int K, int VAR>
+void launch_vdep_inst(vm_vspline* s, const DepositPlan& pl, const double* v, const double* w, long np, double* out)
+{
+    vm_ctx* ctx = s->ctx;
+    static size_t configured[64] = {};
+    size_t& conf = configured[ctx->device & 63];
+    if (pl.smem > conf) {
+        VM_CUDA(cudaFuncSetAttribute(k_v_deposit<K, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+        conf = pl.smem;
+    }
+    k_v_deposit<K, VAR><<<pl.grid, pl.threads, pl.smem, ctx->stream>>>(v, w, np, vcell(s), s->cellpoly, s->npar,
+                                                                      pl.rep_log2, out);
+    VM_LAUNCHED(ctx);
+}
+
+template <int K>
+void launch_vdep_var(vm_vspline* s, const DepositPlan& pl, const double* v, const double* w, long np, double* out)
+{
+    switch (pl.var) {
+        case VAR_PRIV: launch_vdep_inst<K, VAR_PRIV>(s, pl, v, w, np, out); break;
+        case VAR_MATCH: launch_vdep_inst<K, VAR_MATCH>(s, pl, v, w, np, out); break;
+        default: launch_vdep_inst<K, VAR_ATOMIC>(s, pl, v, w, np, out); break;
+    }
+}
+
+#define VM_ORDER_SWITCH(order, ...)                                                         \
+    switch (order) {                                                                        \
+        case 2: { constexpr int K = 2; __VA_ARGS__; } break;                                \
+        case 3: { constexpr int K = 3; __VA_ARGS__; } break;                                \
+        case 4: { constexpr int K = 4; __VA_ARGS__; } break;                                \
+        case 5: { constexpr int K = 5; __VA_ARGS__; } break;                                \
+        case 6: { constexpr int K = 6; __VA_ARGS__; } break;                                \
+        default: throw vm_error(VM_ERR_UNSUPPORTED, "spline order must be in 2..6");        \
+    }
+
+// projection: deposit -> fixed-order reduce -> all-reduce -> M^{-1} -> per-cell polynomials
+void project_dev(vm_vspline* s, const double* v, const double* w, long np)
+{
+    vm_ctx* ctx = s->ctx;
+    DepositPlan pl = plan_deposit(ctx, s->npar, false, VM_DEPOSIT_DETERMINISTIC);
+    double* out = vm_partials(ctx, (size_t)pl.grid * s->npar);
+    VM_ORDER_SWITCH(s->order, launch_vdep_var<K>(s, pl, v, w, np, out));
+    vm_reduce_rows(ctx, out, pl.grid, s->npar, s->rhs);
+    vm_allreduce_sum(ctx, s->rhs, (size_t)s->npar);
+    const int off = s->bc ? 1 : 0;
+    k_v_solve<<<(s->nv + 7) / 8, 256, 0, ctx->stream>>>(s->minv, s->rhs, s->nv, off, s->npar, s->coef);
+    VM_LAUNCHED(ctx);
+    const int tot = s->ncell * s->order;
+    k_v_poly<<<(tot + 255) / 256, 256, 0, ctx->stream>>>(s->coef, s->cellpoly, s->ncell, s->order, s->poly);
+    VM_LAUNCHED(ctx);
+}
+
+void moments_dev(vm_vspline* s, const double* v, long np, int conservative)
+{
+    vm_ctx* ctx = s->ctx;
+    if (conservative) {
+        int grid, threads;
+        geometry(ctx, &grid, &threads);
+        double* out = vm_partials(ctx, (size_t)grid * 8);
+        const size_t smem = (size_t)s->ncell * s->order * sizeof(double);
+        VM_ORDER_SWITCH(s->order, k_v_moments<K><<<grid, threads, smem, ctx->stream>>>(v, np, vcell(s), s->poly, out));
+        VM_LAUNCHED(ctx);
+        k_reduce_rows8<<<1, 256, 0, ctx->stream>>>(out, grid, s->moments);
+        VM_LAUNCHED(ctx);
+        vm_allreduce_sum(ctx, s->moments, 5);
+    }
+    k_clb_coeffs<<<1, 32, 0, ctx->stream>>>(s->moments, conservative);
+    VM_LAUNCHED(ctx);
+}
+
+void rhs_dev(vm_vspline* s, const double* v, const double* w, long np, double nu, int conservative, double* vdot)
+{
+    vm_ctx* ctx = s->ctx;
+    project_dev(s, v, w, np);
+    moments_dev(s, v, np, conservative);
+    int grid, threads;
+    geometry(ctx, &grid, &threads);
+    const size_t smem = (size_t)s->ncell * s->order * sizeof(double);
+    VM_ORDER_SWITCH(s->order, k_v_rhs<K><<<grid, threads, smem, ctx->stream>>>(v, np, vcell(s), s->poly, s->moments, nu, vdot));
+    VM_LAUNCHED(ctx);
+}
+
+double* work_array(vm_particles* p, int i)
+{
+    if (!p->work[i]) VM_CUDA(cudaMalloc(&p->work[i], (size_t)(p->n > 0 ? p->n : 1) * sizeof(double)));
+    return p->work[i];
+}
+
+void check_pair(vm_vspline* s, vm_particles* p, const char* who)
+{
+    if (!s || !p) throw vm_error(VM_ERR_INVALID, std::string(who) + ": NULL handle");
+    if (s->ctx != p->ctx) throw vm_error(VM_ERR_INVALID, std::string(who) + ": spline and particles belong to different contexts");
+}
+
+}  // namespace
+
+extern "C" {
+
+int vm_vspline_create(vm_ctx* ctx, double vmin, double vmax, int nknots, int order, int bc, vm_vspline** out)
+{
+    VM_API_BEGIN(ctx)
+    VM_REQUIRE(ctx != nullptr && out != nullptr, "vm_vspline_create: NULL argument");
+    *out = nullptr;
+    VM_REQUIRE(vmax > vmin, "vm_vspline_create: empty domain");
+    if (order < VM_MIN_ORDER || order > VM_MAX_ORDER) throw vm_error(VM_ERR_UNSUPPORTED, "vm_vspline_create: order must be in 2..6");
+    VM_REQUIRE(bc == 0 || bc == 1, "vm_vspline_create: bc must be 0 (none) or 1 (Dirichlet)");
+    VM_REQUIRE(nknots >= 2 && nknots + order - 2 <= VM_MAX_NBASIS, "vm_vspline_create: nknots out of range");
+    VM_REQUIRE(nknots + order - 2 - (bc ? 2 : 0) >= 1, "vm_vspline_create: empty basis");
+    using vmhost::ld;
+    vm_vspline* s = new vm_vspline();
+    try {
+        const int k = order;
+        s->ctx = ctx;
+        s->a = vmin; s->b = vmax; s->order = k; s->nknots = nknots; s->bc = bc;
+        s->ncell = nknots - 1;
+        s->npar = nknots + k - 2;
+        s->nv = s->npar - (bc ? 2 : 0);
+        s->h = (vmax - vmin) / s->ncell;
+        const ld h = ((ld)vmax - (ld)vmin) / (ld)s->ncell;
+        auto brk = [&](int i) -> ld {
+            if (i <= 0) return (ld)vmin;
+            if (i >= nknots - 1) return (ld)vmax;
+            return (ld)vmin + (ld)i * h;
+        };
+        // exact polynomial pieces per cell and the parent mass matrix
+        std::vector<double> cp((size_t)s->ncell * k * k);
+        std::vector<ld> Mpar((size_t)s->npar * s->npar, 0);
+        for (int c = 0; c < s->ncell; ++c) {
+            ld tl[2 * vmhost::MAXK], A[vmhost::MAXK * vmhost::MAXK];
+            for (int i = 0; i < 2 * k; ++i) tl[i] = brk(c + i - k + 1);
+            const ld hc = brk(c + 1) - brk(c);
+            vmhost::cell_polys(tl, k, brk(c), hc, A);
+            for (int j = 0; j < k * k; ++j) cp[(size_t)c * k * k + j] = (double)A[j];
+            for (int j1 = 0; j1 < k; ++j1)
+                for (int j2 = 0; j2 < k; ++j2)
+                    Mpar[(size_t)(c + j1) * s->npar + (c + j2)] += hc * vmhost::poly_dot(A + j1 * k, A + j2 * k, k);
+        }
+        const int off = bc ? 1 : 0, nv = s->nv;
+        std::vector<ld> M((size_t)nv * nv), Minv;
+        for (int i = 0; i < nv; ++i)
+            for (int j = 0; j < nv; ++j) M[(size_t)i * nv + j] = Mpar[(size_t)(i + off) * s->npar + (j + off)];
+        if (!vmhost::spd_banded_inverse(M, nv, k - 1, Minv)) throw vm_error(VM_ERR_INVALID, "vm_vspline_create: mass matrix is not positive definite");
+        s->mass.resize((size_t)nv * nv);
+        std::vector<double> minv((size_t)nv * nv);
+        for (size_t i = 0; i < (size_t)nv * nv; ++i) { s->mass[i] = (double)M[i]; minv[i] = (double)Minv[i]; }
+
+        VM_CUDA(cudaMalloc(&s->rhs, (size_t)s->npar * sizeof(double)));
+        VM_CUDA(cudaMalloc(&s->coef, (size_t)s->npar * sizeof(double)));
+        VM_CUDA(cudaMalloc(&s->minv, minv.size() * sizeof(double)));
+        VM_CUDA(cudaMalloc(&s->cellpoly, cp.size() * sizeof(double)));
+        VM_CUDA(cudaMalloc(&s->poly, (size_t)s->ncell * k * sizeof(double)));
+        VM_CUDA(cudaMalloc(&s->moments, 16 * sizeof(double)));
+        VM_CUDA(cudaMemsetAsync(s->rhs, 0, (size_t)s->npar * sizeof(double), ctx->stream));
+        VM_CUDA(cudaMemsetAsync(s->coef, 0, (size_t)s->npar * sizeof(double), ctx->stream));
+        VM_CUDA(cudaMemsetAsync(s->poly, 0, (size_t)s->ncell * k * sizeof(double), ctx->stream));
+        VM_CUDA(cudaMemsetAsync(s->moments, 0, 16 * sizeof(double), ctx->stream));
+        VM_CUDA(cudaMemcpyAsync(s->minv, minv.data(), minv.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        VM_CUDA(cudaMemcpyAsync(s->cellpoly, cp.data(), cp.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        VM_CUDA(cudaStreamSynchronize(ctx->stream));
+        VM_REQUIRE((size_t)s->ncell * k * sizeof(double) <= 160 * 1024, "vm_vspline_create: polynomial table exceeds shared memory");
+    } catch (...) {
+        vm_vspline_destroy(s);
+        throw;
+    }
+    *out = s;
+    VM_API_END
+}
+
+int vm_vspline_destroy(vm_vspline* s)
+{
+    if (!s) return VM_OK;
+    cudaSetDevice(s->ctx->device);
+    cudaStreamSynchronize(s->ctx->stream);
+    cudaFree(s->rhs); cudaFree(s->coef); cudaFree(s->minv); cudaFree(s->cellpoly); cudaFree(s->poly);
+    cudaFree(s->moments); cudaFree(s->diag);
+    delete s;
+    return VM_OK;
+}
+
+int vm_vspline_size(vm_vspline* s) { return s ? s->nv : -1; }
+
+int vm_vspline_get_coefficients(vm_vspline* s, double* host)
+{
+    VM_API_BEGIN(s ? s->ctx : nullptr)
+    VM_REQUIRE(s != nullptr && host != nullptr, "vm_vspline_get_coefficients: NULL argument");
+    VM_CUDA(cudaMemcpyAsync(host, s->coef + (s->bc ? 1 : 0), (size_t)s->nv * sizeof(double), cudaMemcpyDeviceToHost, s->ctx->stream));
+    VM_CUDA(cudaStreamSynchronize(s->ctx->stream));
+    VM_API_END
+}
+
+int vm_vspline_set_coefficients(vm_vspline* s, const double* host)
+{
+    VM_API_BEGIN(s ? s->ctx : nullptr)
+    VM_REQUIRE(s != nullptr && host != nullptr, "vm_vspline_set_coefficients: NULL argument");
+    vm_ctx* ctx = s->ctx;
+    VM_CUDA(cudaMemsetAsync(s->coef, 0, (size_t)s->npar * sizeof(double), ctx->stream));
+    VM_CUDA(cudaMemcpyAsync(s->coef + (s->bc ? 1 : 0), host, (size_t)s->nv * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    const int tot = s->ncell * s->order;
+    k_v_poly<<<(tot + 255) / 256, 256, 0, ctx->stream>>>(s->coef, s->cellpoly, s->ncell, s->order, s->poly);
+    VM_LAUNCHED(ctx);
+    VM_CUDA(cudaStreamSynchronize(ctx->stream));
+    VM_API_END
+}
+
+int vm_vspline_get_rhs(vm_vspline* s, double* host)
+{
+    VM_API_BEGIN(s ? s->ctx : nullptr)
+    VM_REQUIRE(s != nullptr && host != nullptr, "vm_vspline_get_rhs: NULL argument");
+    VM_CUDA(cudaMemcpyAsync(host, s->rhs + (s->bc ? 1 : 0), (size_t)s->nv * sizeof(double), cudaMemcpyDeviceToHost, s->ctx->stream));
+    VM_CUDA(cudaStreamSynchronize(s->ctx->stream));
+    VM_API_END
+}
+
+int vm_vspline_get_mass_matrix(vm_vspline* s, double* host)
+{
+    VM_API_BEGIN(s ? s->ctx : nullptr)
+    VM_REQUIRE(s != nullptr && host != nullptr, "vm_vspline_get_mass_matrix: NULL argument");
+    std::memcpy(host, s->mass.data(), s->mass.size() * sizeof(double));
+    VM_API_END
+}
+
+int vm_vproject(vm_vspline* s, vm_particles* p)
+{
+    VM_API_BEGIN(s ? s->ctx : nullptr)
+    check_pair(s, p, "vm_vproject");
+    project_dev(s, p->v, p->w, p->n);
+    VM_API_END
+}
+
+int vm_vspline_eval(vm_vspline* s, const double* v_host, long n, double* f_host, double* df_host)
+{
+    VM_API_BEGIN(s ? s->ctx : nullptr)
+    VM_REQUIRE(s != nullptr && (n == 0 || v_host != nullptr), "vm_vspline_eval: NULL argument");
+    if (n > 0) {
+        vm_ctx* ctx = s->ctx;
+        double* buf = nullptr;
+        VM_CUDA(cudaMalloc(&buf, (size_t)3 * n * sizeof(double)));
+        try {
+            VM_CUDA(cudaMemcpyAsync(buf, v_host, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+            int grid = (int)((n + 255) / 256);
+            if (grid > ctx->sm_count * 4) grid = ctx->sm_count * 4;
+            const size_t smem = (size_t)s->ncell * s->order * sizeof(double);
+            VM_ORDER_SWITCH(s->order, k_v_eval<K><<<grid, 256, smem, ctx->stream>>>(buf, n, vcell(s), s->poly, buf + n, buf + 2 * n));
+            VM_LAUNCHED(ctx);
+            if (f_host) VM_CUDA(cudaMemcpyAsync(f_host, buf + n, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+            if (df_host) VM_CUDA(cudaMemcpyAsync(df_host, buf + 2 * n, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+            VM_CUDA(cudaStreamSynchronize(ctx->stream));
+        } catch (...) { cudaFree(buf); throw; }
+        VM_CUDA(cudaFree(buf));
+    }
+    VM_API_END
+}
+
+int vm_vmoments(vm_vspline* s, vm_particles* p, double* out5, double* A2)
+{
+    VM_API_BEGIN(s ? s->ctx : nullptr)
+    check_pair(s, p, "vm_vmoments");
+    vm_ctx* ctx = s->ctx;
+    moments_dev(s, p->v, p->n, 1);
+    double* host = vm_pinned(ctx, 8);
+    VM_CUDA(cudaMemcpyAsync(host, s->moments, 8 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    VM_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (out5) for (int i = 0; i < 5; ++i) out5[i] = host[i];
+    if (A2) { A2[0] = host[5]; A2[1] = host[6]; }
+    VM_API_END
+}
+
+int vm_lb_rhs(vm_vspline* s, vm_particles* p, double nu, int conservative, double* vdot_host)
+{
+    VM_API_BEGIN(s ? s->ctx : nullptr)
+    check_pair(s, p, "vm_lb_rhs");
+    vm_ctx* ctx = s->ctx;
+    if (!p->a) VM_CUDA(cudaMalloc(&p->a, (size_t)(p->n > 0 ? p->n : 1) * sizeof(double)));
+    rhs_dev(s, p->v, p->w, p->n, nu, conservative, p->a);
+    if (vdot_host) {
+        if (p->n > 0) VM_CUDA(cudaMemcpyAsync(vdot_host, p->a, (size_t)p->n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        VM_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    VM_API_END
+}
+
+int vm_lb_rk438_run(vm_vspline* s, vm_particles* p, double dt, int nsteps, double nu, int conservative,
+                    int diag_every, double* diag_host)
+{
+    VM_API_BEGIN(s ? s->ctx : nullptr)
+    check_pair(s, p, "vm_lb_rk438_run");
+    VM_REQUIRE(nsteps >= 0 && diag_every >= 0, "vm_lb_rk438_run: bad argument");
+    VM_REQUIRE(diag_every == 0 || diag_host != nullptr, "vm_lb_rk438_run: diag_host is NULL");
+    vm_ctx* ctx = s->ctx;
+    const long np = p->n;
+    const int nrows = diag_every > 0 ? nsteps / diag_every + 1 : 0;
+    if (nrows > s->diag_rows) {
+        VM_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (s->diag) VM_CUDA(cudaFree(s->diag));
+        s->diag = nullptr; s->diag_rows = 0;
+        VM_CUDA(cudaMalloc(&s->diag, (size_t)nrows * 4 * sizeof(double)));
+        s->diag_rows = nrows;
+    }
+    int grid, threads;
+    geometry(ctx, &grid, &threads);
+    int row = 0;
+    auto record = [&](double t) {
+        double* out = vm_partials(ctx, (size_t)grid * 8);
+        k_v_sums<<<grid, threads, 0, ctx->stream>>>(p->v, np, out);
+        VM_LAUNCHED(ctx);
+        k_reduce_rows8<<<1, 256, 0, ctx->stream>>>(out, grid, s->moments + 8);
+        VM_LAUNCHED(ctx);
+        vm_allreduce_sum(ctx, s->moments + 8, 2);
+        k_v_store_diag<<<1, 32, 0, ctx->stream>>>(s->diag + (size_t)row * 4, t, s->moments + 8);
+        VM_LAUNCHED(ctx);
+        ++row;
+    };
+    if (nrows > 0) record(0.0);
+    if (np > 0 && nsteps > 0) {
+        double *k1 = work_array(p, 0), *k2 = work_array(p, 1), *k3 = work_array(p, 2), *k4 = work_array(p, 3),
+               *q = work_array(p, 4);
+        // classical 3/8 rule (GeometricIntegrators RK438): a21=1/3; a31=-1/3, a32=1; a41=1, a42=-1, a43=1
+        const double a21 = 1.0 / 3.0, a31 = -1.0 / 3.0;
+        for (int st = 1; st <= nsteps; ++st) {
+            rhs_dev(s, p->v, p->w, np, nu, conservative, k1);
+            k_rk_combine<<<grid, threads, 0, ctx->stream>>>(p->v, k1, nullptr, nullptr, nullptr, a21, 0, 0, 0, dt, np, q);
+            VM_LAUNCHED(ctx);
+            rhs_dev(s, q, p->w, np, nu, conservative, k2);
+            k_rk_combine<<<grid, threads, 0, ctx->stream>>>(p->v, k1, k2, nullptr, nullptr, a31, 1.0, 0, 0, dt, np, q);
+            VM_LAUNCHED(ctx);
+            rhs_dev(s, q, p->w, np, nu, conservative, k3);
+            k_rk_combine<<<grid, threads, 0, ctx->stream>>>(p->v, k1, k2, k3, nullptr, 1.0, -1.0, 1.0, 0, dt, np, q);
+            VM_LAUNCHED(ctx);
+            rhs_dev(s, q, p->w, np, nu, conservative, k4);
+            k_rk_combine<<<grid, threads, 0, ctx->stream>>>(p->v, k1, k2, k3, k4, 0.125, 0.375, 0.375, 0.125, dt, np, p->v);
+            VM_LAUNCHED(ctx);
+            if (diag_every > 0 && st % diag_every == 0) record(dt * st);
+        }
+    }
+    if (nrows > 0) {
+        double* host = vm_pinned(ctx, (size_t)nrows * 4);
+        VM_CUDA(cudaMemcpyAsync(host, s->diag, (size_t)row * 4 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        VM_CUDA(cudaStreamSynchronize(ctx->stream));
+        for (int i = 0; i < nrows * 4; ++i) diag_host[i] = i < row * 4 ? host[i] : 0.0;
+    }
+    VM_API_END
+}
+
+}  // extern "C"
