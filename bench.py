@@ -1,0 +1,329 @@
+#!/usr/bin/env python
+"""bench.py -- particle-steps/s of the Vlasov-Poisson spline-PIC step on B200 (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+  python bench.py --impl reference --gpus N --steps K ...   # CPU arm: C restatement of the reference algorithm
+
+Workload (config.workload): bump-on-tail, BASELINE.json configs[1]: 1e8 particles TOTAL (strong
+scaling over N GPUs), periodic cubic B-splines (degree 3 = order 4), n_h = 16, L = 2 pi / 0.3,
+dt = 0.1 (scripts/bump_on_tail.jl:14-32 scaled to 1e8 particles), synthetic Philox load.
+
+A "step" = one Strang step: E gather -> kick -> drift -> charge deposition -> all-reduce -> Poisson solve.
+`value`  : particles resident in HBM, K steps timed with CUDA events on the library's stream.
+`e2e`    : same K steps through the host API with HOST (pinned) particle arrays: upload of x,v,w,
+           K steps with a [W,K,M] diagnostics read-back, download of x,v -- all inside the timed region.
+`roofline`: the fused push+deposit kernel, 40 algorithmic bytes per particle per launch, timed per
+           launch with CUDA event brackets inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import sys
+import tempfile
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+N_TOTAL = 100_000_000
+N_BASIS, ORDER, DT = 16, 4, 0.1
+EPS, KAPPA, ALPHA, SIGMA, V0 = 0.03, 0.3, 0.1, 0.5, 4.5
+L_DOMAIN = 2 * math.pi / KAPPA
+ALG_BYTES_PER_PARTICLE = 40          # read x,v,w (24 B) + write x,v (16 B); SURVEY 8(d)
+SEED = 20240601
+
+
+def peaks():
+    f = ROOT / "MEASURED_PEAKS.json"
+    if f.exists():
+        try:
+            return float(json.loads(f.read_text())["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return 6650.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU during the timed region (NVML)."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.sm_max = index, [], set(), None
+        self._stop_evt = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.sm_max = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def physical_gpu_index(local_rank: int) -> int:
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        try:
+            return int(vis.split(",")[local_rank])
+        except Exception:
+            pass
+    return local_rank
+
+
+# ------------------------------------------------------------------ CPU arm --
+def native_oracle():
+    """-march=native build of the oracle for the timed CPU baseline (built on the machine that runs it)."""
+    from oracle import vm_oracle as orc
+    out = Path(tempfile.gettempdir()) / f"libvm_oracle_native_{os.getpid()}.so"
+    try:
+        orc.build(native_out=str(out))
+        return orc, orc.lib(str(out))
+    except Exception:
+        return orc, orc.lib()
+
+
+def sample_particles(n, seed=SEED):
+    """Bump-on-tail load for the CPU arm (numpy; same distribution as the device fill)."""
+    rng = np.random.default_rng(seed)
+    u = rng.uniform(size=n)
+    x = u * L_DOMAIN
+    for _ in range(40):
+        x -= (x - (EPS / KAPPA) * np.sin(KAPPA * x) - u * L_DOMAIN) / (1 - EPS * np.cos(KAPPA * x))
+    v = rng.standard_normal(n)
+    tail = rng.uniform(size=n) > 1 - ALPHA
+    v[tail] = v[tail] * SIGMA + V0
+    w = np.full(n, L_DOMAIN / n)
+    return x, v, w
+
+
+def cpu_baseline(target_seconds=12.0):
+    """C restatement of the reference algorithm on the host cores, bounded sample of the same workload."""
+    orc, nlib = native_oracle()
+    threads = orc.max_threads(nlib)
+    n_s = 4_000_000
+    x, v, w = sample_particles(n_s)
+    t0 = time.perf_counter()
+    orc.baseline_vp_steps(x, v, w, DT, 1, 0.0, L_DOMAIN, N_BASIS, ORDER, 0, threads, nlib)   # warm-up + calibration
+    t1 = time.perf_counter() - t0
+    steps = int(max(2, min(40, target_seconds / max(t1, 1e-3))))
+    t0 = time.perf_counter()
+    orc.baseline_vp_steps(x, v, w, DT, steps, 0.0, L_DOMAIN, N_BASIS, ORDER, 0, threads, nlib)
+    dt_all = time.perf_counter() - t0
+    # single thread (the reference itself is single-threaded), smaller sample
+    n_1 = 500_000
+    t0 = time.perf_counter()
+    orc.baseline_vp_steps(x[:n_1].copy(), v[:n_1].copy(), w[:n_1].copy(), DT, 2, 0.0, L_DOMAIN, N_BASIS, ORDER, 0, 1, nlib)
+    dt_1 = time.perf_counter() - t0
+    return {"value": n_s * steps / dt_all, "unit": "particle-steps/s", "cores": threads, "kind": "port",
+            "sample": f"{n_s} particles x {steps} Strang steps (2 deposits+2 solves+2 gathers each, as the reference), "
+                      f"OpenMP {threads} threads, C restatement of the reference algorithm (Julia unavailable)",
+            "single_thread_value": n_1 * 2 / dt_1}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    orc, nlib = native_oracle()
+    threads = orc.max_threads(nlib)
+    n_s = 4_000_000                              # bounded sample of the 1e8-particle workload per step
+    x, v, w = sample_particles(n_s)
+    for _ in range(args.warmup):
+        orc.baseline_vp_steps(x, v, w, DT, 1, 0.0, L_DOMAIN, N_BASIS, ORDER, 0, threads, nlib)
+    t0 = time.perf_counter()
+    orc.baseline_vp_steps(x, v, w, DT, args.steps, 0.0, L_DOMAIN, N_BASIS, ORDER, 0, threads, nlib)
+    dt = time.perf_counter() - t0
+    val = n_s * args.steps / dt
+    sample = (f"{n_s}-particle sample of the 1e8 workload per step, OpenMP {threads} threads; "
+              "C restatement of the reference algorithm (Julia toolchain unavailable)")
+    print(json.dumps({
+        "impl": "reference", "metric": "particle-steps/sec", "value": val, "unit": "particle-steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": val, "unit": "particle-steps/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def workload_config(ngpus):
+    return {"workload": "bump_on_tail_1d1v_1e8", "particles_total": N_TOTAL, "n_basis": N_BASIS, "spline_order": ORDER,
+            "dt": DT, "domain_length": L_DOMAIN, "field_source": "state", "deposit": "deterministic",
+            "sharding": f"particles/{ngpus}", "l2": "inputs_larger_than_L2"}
+
+
+# ------------------------------------------------------------------ GPU arm --
+def run_gpu(args):
+    from __graft_entry__ import load_package
+    vm = load_package()
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group(backend="gloo")      # host-side rendezvous/barrier only
+    ctx = vm.init_distributed_context(local)
+    ntot = args.particles
+    lo, hi = vm.shard_bounds(ntot, rank, world)
+    nloc = hi - lo
+
+    def barrier():
+        ctx.sync()
+        if world > 1:
+            dist.barrier()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
+
+    fld = vm.DeviceField(ctx, 0.0, L_DOMAIN, ORDER, N_BASIS, 0)
+    p = vm.DeviceParticles(ctx, nloc)
+    p.fill(vm._lib.VM_FILL_BUMP_ON_TAIL, [EPS, KAPPA, ALPHA, SIGMA, V0], SEED, lo, ntot)
+    flags = vm._lib.VM_RUN_ATOMIC_DEPOSIT if args.atomic else 0
+
+    # ---------------- device-resident timing ----------------
+    fld.run(p, DT, args.warmup, 0, flags, 1.0)
+    ctx.set_tuning("profile", 1)
+    ctx.profile_read()
+    sampler = ClockSampler(physical_gpu_index(local))
+    barrier()
+    l0 = ctx.launch_count()
+    sampler.start()
+    ctx.event_record(0)
+    fld.run(p, DT, args.steps, 0, flags, 1.0)
+    ctx.event_record(1)
+    barrier()
+    clocks = sampler.stop()
+    ms = max_over_ranks(ctx.event_elapsed_ms(0, 1))
+    launches = ctx.launch_count() - l0
+    kn, kms = ctx.profile_read()
+    ctx.set_tuning("profile", 0)
+    value = ntot * args.steps / (ms * 1e-3)
+
+    peak, peak_src = peaks()
+    roofline = None
+    if kn > 0:
+        achieved = ALG_BYTES_PER_PARTICLE * nloc / (kms / kn * 1e-3) / 1e9
+        traffic = None
+        tf = ROOT / "profiles" / "traffic.json"
+        if tf.exists():
+            try:
+                traffic = json.loads(tf.read_text()).get("k_vp_pass_push_deposit_bytes_per_particle")
+                traffic = traffic * nloc if traffic is not None else None
+            except Exception:
+                traffic = None
+        roofline = {"bound": "hbm", "kernel": "k_vp_pass<4,PRIV,PUSH_DEPOSIT>", "achieved": achieved, "peak": peak,
+                    "unit": "GB/s", "frac": achieved / peak, "peak_source": f"of {peak_src}",
+                    "traffic": traffic, "launches_timed": kn, "avg_launch_ms": kms / kn,
+                    "algorithmic_bytes_per_launch": ALG_BYTES_PER_PARTICLE * nloc}
+
+    # ---------------- end-to-end through host buffers ----------------
+    hx = torch.empty(nloc, dtype=torch.float64).pin_memory()
+    hv = torch.empty(nloc, dtype=torch.float64).pin_memory()
+    hw = torch.empty(nloc, dtype=torch.float64).pin_memory()
+    p.fill(vm._lib.VM_FILL_BUMP_ON_TAIL, [EPS, KAPPA, ALPHA, SIGMA, V0], SEED, lo, ntot)
+    p.download(out=(hx.numpy(), hv.numpy(), hw.numpy()))
+    e2e_steps = args.steps
+
+    def e2e_once():
+        p.upload(hx.numpy(), hv.numpy(), hw.numpy())                     # H2D 24 B/particle
+        d = fld.run(p, DT, e2e_steps, e2e_steps, flags, 1.0)             # K steps + [W,K,M] rows read back
+        p.download(w=False, out=(hx.numpy(), hv.numpy(), None))          # D2H 16 B/particle
+        return d
+
+    e2e_once()                                                           # warm-up (page-locks, allocations)
+    p.fill(vm._lib.VM_FILL_BUMP_ON_TAIL, [EPS, KAPPA, ALPHA, SIGMA, V0], SEED, lo, ntot)
+    p.download(out=(hx.numpy(), hv.numpy(), hw.numpy()))
+    barrier()
+    t0 = time.perf_counter()
+    ctx.event_record(2)
+    diag = e2e_once()
+    ctx.event_record(3)
+    barrier()
+    wall = time.perf_counter() - t0
+    e2e_ms = max_over_ranks(max(ctx.event_elapsed_ms(2, 3), 0.0))
+    e2e = {"value": ntot * e2e_steps / (e2e_ms * 1e-3), "unit": "particle-steps/s",
+           "h2d_bytes_per_step": 24 * ntot / e2e_steps, "d2h_bytes_per_step": (16 * ntot + 2 * 32 * world) / e2e_steps,
+           "steps_per_call": e2e_steps, "ms_per_call": e2e_ms, "wall_ms": wall * 1e3,
+           "what": "upload x,v,w from pinned host arrays + K fused steps + diagnostics read-back + download x,v "
+                   "(vm_particles_upload_soa / vm_vp_run / vm_particles_download_soa)",
+           "energy_drift": float(abs((diag[-1, 0] + diag[-1, 1]) - (diag[0, 0] + diag[0, 1])) / (diag[0, 0] + diag[0, 1]))}
+
+    cpu = None
+    if world == 1 and rank == 0 and not args.no_cpu:
+        try:
+            cpu = cpu_baseline()
+        except Exception as exc:   # the CPU leg must never take the GPU number down with it
+            cpu = {"error": repr(exc)}
+
+    if rank == 0:
+        cfg = workload_config(world)
+        cfg["particles_total"] = ntot
+        print(json.dumps({
+            "metric": "particle-steps/sec", "value": value, "unit": "particle-steps/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "step_hbm_frac": ALG_BYTES_PER_PARTICLE * nloc * args.steps / (ms * 1e-3) / 1e9 / peak,
+        }))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--particles", type=int, default=N_TOTAL)
+    ap.add_argument("--atomic", action="store_true", help="use the shared-atomic deposit variant (A/B)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

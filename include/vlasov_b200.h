@@ -64,7 +64,7 @@ int vm_sync(vm_ctx* ctx);
 int vm_ctx_device_info(vm_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor,
                        size_t* free_bytes, size_t* total_bytes);
 /* Tuning knobs (defaults are chosen from the device and problem size).
- * key: "ctas_per_sm", "threads_per_cta", "replicas" (0 = auto), "use_graph". */
+ * key: "ctas_per_sm", "threads_per_cta", "replicas" (0 = auto), "profile" (see vm_profile_read). */
 int vm_ctx_set_tuning(vm_ctx* ctx, const char* key, int value);
 
 /* Multi-GPU, one process per GPU.  Rank 0 obtains a 128-byte NCCL unique id
@@ -78,6 +78,12 @@ int vm_event_record(vm_ctx* ctx, int slot);
 int vm_event_elapsed_ms(vm_ctx* ctx, int slot_start, int slot_stop, double* ms);
 /* Number of kernels this context has launched so far. */
 unsigned long long vm_launch_count(vm_ctx* ctx);
+/* Per-launch device timing of the dominant kernel (the fused gather+kick+drift+deposit pass of
+ * vm_vp_run, or the deposit pass of vm_deposit / vm_lb_rhs): when tuning key "profile" is 1 every
+ * such launch is bracketed by CUDA events on the context's stream.  vm_profile_read synchronises,
+ * returns the number of bracketed launches and their summed duration since the last read, and
+ * resets the counters. */
+int vm_profile_read(vm_ctx* ctx, long* launches, double* total_ms);
 
 /* ------------------------------------------------------------- particles --
  * Replaces ParticleDistribution{1,1} (src/distributions/particle_distribution.jl:2-24),

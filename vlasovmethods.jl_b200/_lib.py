@@ -33,6 +33,7 @@ SIGNATURES = {
     "vm_event_record": (_i, [_vp, _i]),
     "vm_event_elapsed_ms": (_i, [_vp, _i, _i, C.POINTER(_d)]),
     "vm_launch_count": (C.c_ulonglong, [_vp]),
+    "vm_profile_read": (_i, [_vp, C.POINTER(_l), C.POINTER(_d)]),
     "vm_particles_create": (_i, [_vp, _l, C.POINTER(_vp)]),
     "vm_particles_destroy": (_i, [_vp]),
     "vm_particles_size": (_l, [_vp]),

@@ -79,6 +79,12 @@ class Context:
     def launch_count(self) -> int:
         return int(L.lib().vm_launch_count(self._h))
 
+    def profile_read(self):
+        """(launches, total_ms) of the event-bracketed dominant kernel since the last read."""
+        n, ms = C.c_long(), C.c_double()
+        L.check(L.lib().vm_profile_read(self._h, C.byref(n), C.byref(ms)), self._h)
+        return n.value, ms.value
+
 
 _default_ctx = None
 

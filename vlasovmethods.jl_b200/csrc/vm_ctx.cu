@@ -53,6 +53,17 @@ void vm_launch_geometry(vm_ctx* ctx, int* grid, int* threads)
     *grid = ctx->sm_count * c;
 }
 
+void vm_prof_mark(vm_ctx* ctx)
+{
+    if (!ctx->profile) return;
+    if (ctx->prof_used == ctx->prof_events.size()) {
+        cudaEvent_t e;
+        VM_CUDA(cudaEventCreate(&e));
+        ctx->prof_events.push_back(e);
+    }
+    VM_CUDA(cudaEventRecord(ctx->prof_events[ctx->prof_used++], ctx->stream));
+}
+
 // ------------------------------------------------------------------ NCCL ----
 // libnccl.so.2 is resolved at run time (the copy bundled with PyTorch is already
 // mapped in a torchrun process; a Julia host would have NCCL_jll's).  Only the
@@ -162,6 +173,7 @@ int vm_ctx_destroy(vm_ctx* ctx)
         try { nccl_api().CommDestroy(ctx->nccl_comm); } catch (...) {}
     }
     for (int i = 0; i < VM_MAX_EVENTS; ++i) if (ctx->events[i]) cudaEventDestroy(ctx->events[i]);
+    for (cudaEvent_t e : ctx->prof_events) cudaEventDestroy(e);
     if (ctx->partials) cudaFree(ctx->partials);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     cudaStreamDestroy(ctx->stream);
@@ -206,7 +218,7 @@ int vm_ctx_set_tuning(vm_ctx* ctx, const char* key, int value)
         VM_REQUIRE(value == 0 || (value >= 1 && value <= 32 && (value & (value - 1)) == 0), "replicas must be a power of two <= 32");
         ctx->replicas = value;
     }
-    else if (k == "use_graph") ctx->use_graph = value;
+    else if (k == "profile") ctx->profile = value;
     else throw vm_error(VM_ERR_INVALID, "unknown tuning key: " + k);
     VM_API_END
 }
@@ -271,6 +283,24 @@ int vm_event_elapsed_ms(vm_ctx* ctx, int a, int b, double* ms)
 }
 
 unsigned long long vm_launch_count(vm_ctx* ctx) { return ctx ? ctx->launches : 0ull; }
+
+int vm_profile_read(vm_ctx* ctx, long* launches, double* total_ms)
+{
+    VM_API_BEGIN(ctx)
+    VM_REQUIRE(ctx != nullptr, "vm_profile_read: ctx is NULL");
+    VM_CUDA(cudaStreamSynchronize(ctx->stream));
+    double tot = 0.0;
+    const size_t pairs = ctx->prof_used / 2;
+    for (size_t i = 0; i < pairs; ++i) {
+        float ms = 0.f;
+        VM_CUDA(cudaEventElapsedTime(&ms, ctx->prof_events[2 * i], ctx->prof_events[2 * i + 1]));
+        tot += ms;
+    }
+    ctx->prof_used = 0;
+    if (launches) *launches = (long)pairs;
+    if (total_ms) *total_ms = tot;
+    VM_API_END
+}
 
 }  // extern "C"
 

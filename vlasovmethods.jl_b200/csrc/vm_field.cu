@@ -32,10 +32,14 @@ __global__ void __launch_bounds__(256) k_reduce_rows(const double* __restrict__ 
     }
 }
 
-// phi = G (*) (rhs - mean(rhs)),  dcoef = GD (*) (rhs - mean(rhs))   (circular convolutions)
+// phi = G (*) (rhs - mean(rhs))  (circular convolution with the pseudo-inverse kernel G), and
+// dcoef_m = (phi_{m+1} - phi_m) / h, the coefficients of the derivative spline (E = -phi').
+// Each lane accumulates phi_i and phi_{i+1} with the same chunking over j, so the phi_{i+1} it uses
+// is bit-identical to the phi_{i+1} its neighbour stores: dcoef is a pure function of the stored
+// phi (same bits as k_dcoef_from_phi), as the reference's ExternalField/PoissonField test demands.
 // Every CTA recomputes the mean in the same fixed order, so all CTAs (and all ranks) agree bitwise.
 __global__ void __launch_bounds__(256) k_poisson_solve(const double* __restrict__ rhs, const double* __restrict__ G,
-                                                       const double* __restrict__ GD, int n,
+                                                       int n, double inv_h,
                                                        double* __restrict__ phi, double* __restrict__ dcoef)
 {
     extern __shared__ double r[];          // n
@@ -57,26 +61,29 @@ __global__ void __launch_bounds__(256) k_poisson_solve(const double* __restrict_
     const int i = blockIdx.x * 32 + lane;
     const int len = (n + 7) / 8;
     const int j0 = warp * len, j1 = min(n, j0 + len);
-    double ap = 0.0, ad = 0.0;
+    double a0 = 0.0, a1 = 0.0;             // partial sums of phi_i and phi_{i+1}
     if (i < n) {
         int idx = i - j0;
         if (idx < 0) idx += n;
+        double g1 = __ldg(G + (idx + 1 == n ? 0 : idx + 1));
         for (int j = j0; j < j1; ++j) {
             const double rj = r[j];
-            ap = fma(__ldg(G + idx), rj, ap);
-            ad = fma(__ldg(GD + idx), rj, ad);
+            const double g0 = __ldg(G + idx);
+            a0 = fma(g0, rj, a0);
+            a1 = fma(g1, rj, a1);
+            g1 = g0;
             idx = (idx == 0) ? n - 1 : idx - 1;
         }
     }
-    red[0][warp][lane] = ap;
-    red[1][warp][lane] = ad;
+    red[0][warp][lane] = a0;
+    red[1][warp][lane] = a1;
     __syncthreads();
     if (warp == 0 && i < n) {
-        double p = 0.0, d = 0.0;
+        double p0 = 0.0, p1 = 0.0;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) { p += red[0][q][lane]; d += red[1][q][lane]; }
-        phi[i] = p;
-        dcoef[i] = d;
+        for (int q = 0; q < 8; ++q) { p0 += red[0][q][lane]; p1 += red[1][q][lane]; }
+        phi[i] = p0;
+        dcoef[i] = (p1 - p0) * inv_h;
     }
 }
 
@@ -172,7 +179,7 @@ void vm_field_solve_local(vm_field* f, bool allreduce)
 {
     vm_ctx* ctx = f->ctx;
     if (allreduce) vm_allreduce_sum(ctx, f->rhs, (size_t)f->n);
-    k_poisson_solve<<<(f->n + 31) / 32, 256, (size_t)f->n * sizeof(double), ctx->stream>>>(f->rhs, f->G, f->GD, f->n,
+    k_poisson_solve<<<(f->n + 31) / 32, 256, (size_t)f->n * sizeof(double), ctx->stream>>>(f->rhs, f->G, f->n, f->map.inv_h,
                                                                                           f->phi, f->dcoef);
     VM_LAUNCHED(ctx);
 }
@@ -252,23 +259,18 @@ int vm_field_create(vm_ctx* ctx, double a, double b, int order, int n_basis, int
         }
         std::vector<ld> G;
         if (!vmhost::circulant_pinv(sts, k, n, G)) throw vm_error(VM_ERR_INVALID, "vm_field_create: stiffness matrix is not positive semi-definite");
-        std::vector<double> Gd(n), GDd(n);
-        for (int m = 0; m < n; ++m) {
-            Gd[m] = (double)G[m];
-            GDd[m] = (double)((G[(m + 1) % n] - G[m]) / h);
-        }
+        std::vector<double> Gd(n);
+        for (int m = 0; m < n; ++m) Gd[m] = (double)G[m];
         const size_t nb = (size_t)n * sizeof(double);
         VM_CUDA(cudaMalloc(&f->rhs, nb + (VM_DIAG_COLS + 4) * sizeof(double)));
         VM_CUDA(cudaMalloc(&f->phi, nb));
         VM_CUDA(cudaMalloc(&f->dcoef, nb));
         VM_CUDA(cudaMalloc(&f->G, nb));
-        VM_CUDA(cudaMalloc(&f->GD, nb));
         VM_CUDA(cudaMalloc(&f->stencil_s, k * sizeof(double)));
         VM_CUDA(cudaMemsetAsync(f->rhs, 0, nb + (VM_DIAG_COLS + 4) * sizeof(double), ctx->stream));
         VM_CUDA(cudaMemsetAsync(f->phi, 0, nb, ctx->stream));
         VM_CUDA(cudaMemsetAsync(f->dcoef, 0, nb, ctx->stream));
         upload(ctx, f->G, Gd);
-        upload(ctx, f->GD, GDd);
         upload(ctx, f->stencil_s, st);
     } catch (...) {
         vm_field_destroy(f);
@@ -283,7 +285,7 @@ int vm_field_destroy(vm_field* f)
     if (!f) return VM_OK;
     cudaSetDevice(f->ctx->device);
     cudaStreamSynchronize(f->ctx->stream);
-    cudaFree(f->rhs); cudaFree(f->phi); cudaFree(f->dcoef); cudaFree(f->G); cudaFree(f->GD);
+    cudaFree(f->rhs); cudaFree(f->phi); cudaFree(f->dcoef); cudaFree(f->G);
     cudaFree(f->stencil_s); cudaFree(f->diag);
     delete f;
     return VM_OK;

@@ -44,7 +44,10 @@ struct vm_ctx {
     unsigned long long launches = 0;
     cudaEvent_t events[VM_MAX_EVENTS] = {};
     // tuning (0 = auto)
-    int ctas_per_sm = 0, threads_per_cta = 0, replicas = 0, use_graph = 0;
+    int ctas_per_sm = 0, threads_per_cta = 0, replicas = 0, profile = 0;
+    // per-launch event brackets of the dominant kernel (profile == 1)
+    std::vector<cudaEvent_t> prof_events;   // pairs: [2i] start, [2i+1] stop
+    size_t prof_used = 0;                    // events in use since the last read
     // communicator (one process per GPU)
     void* nccl_comm = nullptr;
     int rank = 0, nranks = 1;
@@ -79,7 +82,7 @@ struct vm_field {
     int order = 0, n = 0, shift = 0;
     CellMap map{};
     double *rhs = nullptr, *phi = nullptr, *dcoef = nullptr;  // device, n each
-    double *G = nullptr, *GD = nullptr;                       // device: circulant pseudo-inverse kernels
+    double *G = nullptr;                                      // device: circulant pseudo-inverse kernel (first column)
     double *stencil_s = nullptr;                              // device: stiffness stencil, 2k-1 entries
     double *diag = nullptr;                                   // device: [W, K, M, sum_w] rows
     int diag_rows = 0;
@@ -107,6 +110,7 @@ double* vm_partials(vm_ctx* ctx, size_t elems);   // grow-only device scratch
 double* vm_pinned(vm_ctx* ctx, size_t elems);     // grow-only pinned host scratch
 void vm_allreduce_sum(vm_ctx* ctx, double* dev, size_t count);  // no-op when nranks == 1
 void vm_launch_geometry(vm_ctx* ctx, int* grid, int* threads);
+void vm_prof_mark(vm_ctx* ctx);   // records the next event of a start/stop pair when profiling is on
 
 #define VM_API_BEGIN(ctxexpr)          \
     vm_ctx* ctx__ = (ctxexpr);         \

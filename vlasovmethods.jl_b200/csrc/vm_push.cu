@@ -350,7 +350,8 @@ void vm_gather_dev(vm_field* f, const double* x_dev, long np, double* e_dev, dou
 }
 
 // One particle pass with deposition; leaves the LOCAL (this rank's) deposit in f->rhs[0..n).
-static void pass_with_deposit(vm_field* f, vm_particles* p, int pass_mode, int deposit_mode, PassParams P)
+static void pass_with_deposit(vm_field* f, vm_particles* p, int pass_mode, int deposit_mode, PassParams P,
+                              bool prof_deposit = false)
 {
     vm_ctx* ctx = f->ctx;
     const int n = f->n;
@@ -367,11 +368,15 @@ static void pass_with_deposit(vm_field* f, vm_particles* p, int pass_mode, int d
     } else {
         out = vm_partials(ctx, (size_t)pl.grid * ncols);
     }
+    // the dominant kernel of its caller: the fused pass inside vm_vp_run, the deposit pass elsewhere
+    const bool prof = (pass_mode == MODE_PUSH_DEPOSIT) || (pass_mode == MODE_DEPOSIT && prof_deposit);
+    if (prof) vm_prof_mark(ctx);
     switch (pass_mode) {
         case MODE_DEPOSIT: launch_pass<MODE_DEPOSIT>(ctx, f->order, pl, p->x, p->v, p->w, f->dcoef, out, P); break;
         case MODE_PUSH_DEPOSIT: launch_pass<MODE_PUSH_DEPOSIT>(ctx, f->order, pl, p->x, p->v, p->w, f->dcoef, out, P); break;
         default: launch_pass<MODE_DRIFT_DEPOSIT>(ctx, f->order, pl, p->x, p->v, p->w, f->dcoef, out, P); break;
     }
+    if (prof) vm_prof_mark(ctx);
     if (pl.var != VAR_ATOMIC) vm_field_reduce_rows(f, out, pl.grid, ncols, f->rhs);
 }
 
@@ -402,7 +407,7 @@ int vm_deposit(vm_field* f, vm_particles* p, int mode)
     check_pair(f, p, "vm_deposit");
     VM_REQUIRE(mode == VM_DEPOSIT_DETERMINISTIC || mode == VM_DEPOSIT_ATOMIC, "vm_deposit: unknown mode");
     PassParams P{};
-    pass_with_deposit(f, p, MODE_DEPOSIT, mode, P);
+    pass_with_deposit(f, p, MODE_DEPOSIT, mode, P, true);
     VM_API_END
 }
 

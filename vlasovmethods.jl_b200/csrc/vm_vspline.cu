@@ -358,7 +358,9 @@ void project_dev(vm_vspline* s, const double* v, const double* w, long np)
     vm_ctx* ctx = s->ctx;
     DepositPlan pl = plan_deposit(ctx, s->npar, false, VM_DEPOSIT_DETERMINISTIC);
     double* out = vm_partials(ctx, (size_t)pl.grid * s->npar);
+    vm_prof_mark(ctx);
     VM_ORDER_SWITCH(s->order, launch_vdep_var<K>(s, pl, v, w, np, out));
+    vm_prof_mark(ctx);
     vm_reduce_rows(ctx, out, pl.grid, s->npar, s->rhs);
     vm_allreduce_sum(ctx, s->rhs, (size_t)s->npar);
     const int off = s->bc ? 1 : 0;
