@@ -26,8 +26,12 @@ struct VCell {
 
 __device__ __forceinline__ bool vcell_of(const VCell& m, double v, int& c, double& xi)
 {
-    const double t = fma(v, m.inv_h, m.off);
-    if (!(t >= 0.0 && t <= (double)m.ncell)) return false;   // outside [vmin, vmax] (or NaN): no contribution
+    double t = fma(v, m.inv_h, m.off);
+    // outside [vmin, vmax] (or NaN): no contribution.  The end points themselves may land a few ulp
+    // outside [0, ncell] after the affine map, so the test carries that rounding slack.
+    const double slack = 2e-15 * (double)m.ncell;
+    if (!(t >= -slack && t <= (double)m.ncell + slack)) return false;
+    t = fmin(fmax(t, 0.0), (double)m.ncell);
     c = min(__double2int_rd(t), m.ncell - 1);
     xi = t - (double)c;
     return true;
