@@ -168,7 +168,7 @@ def run_reference(args):
     val = n_s * args.steps / dt
     sample = (f"{n_s}-particle sample of the 1e8 workload per step, OpenMP {threads} threads; "
               "C restatement of the reference algorithm (Julia toolchain unavailable)")
-    print(json.dumps({
+    emit(({
         "impl": "reference", "metric": "particle-steps/sec", "value": val, "unit": "particle-steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -296,7 +296,7 @@ def run_gpu(args):
     if rank == 0:
         cfg = workload_config(world)
         cfg["particles_total"] = ntot
-        print(json.dumps({
+        emit(({
             "metric": "particle-steps/sec", "value": value, "unit": "particle-steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
@@ -308,7 +308,17 @@ def run_gpu(args):
         dist.destroy_process_group()
 
 
+def emit(obj):
+    """The ONE JSON line goes to the real stdout; everything else (NCCL banners, torchrun notes) was
+    redirected to stderr at start-up."""
+    os.write(_REAL_STDOUT, (json.dumps(obj) + "\n").encode())
+
+
+_REAL_STDOUT = os.dup(1)
+
+
 def main():
+    os.dup2(2, 1)          # libraries that print to fd 1 (NCCL version banner) must not corrupt the JSON line
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)

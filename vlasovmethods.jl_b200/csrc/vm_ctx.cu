@@ -157,6 +157,8 @@ int vm_ctx_create(int device, vm_ctx** out)
         c->smem_optin = prop.sharedMemPerBlockOptin;
         VM_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         for (int i = 0; i < VM_MAX_EVENTS; ++i) VM_CUDA(cudaEventCreate(&c->events[i]));
+        VM_CUDA(cudaMalloc(&c->ticket, sizeof(unsigned)));
+        VM_CUDA(cudaMemset(c->ticket, 0, sizeof(unsigned)));
         *out = c;
     }
     catch (const vm_error& e) { vm_set_error(ctx__, e.what()); return e.code; }
@@ -175,6 +177,7 @@ int vm_ctx_destroy(vm_ctx* ctx)
     for (int i = 0; i < VM_MAX_EVENTS; ++i) if (ctx->events[i]) cudaEventDestroy(ctx->events[i]);
     for (cudaEvent_t e : ctx->prof_events) cudaEventDestroy(e);
     if (ctx->partials) cudaFree(ctx->partials);
+    if (ctx->ticket) cudaFree(ctx->ticket);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -219,6 +222,7 @@ int vm_ctx_set_tuning(vm_ctx* ctx, const char* key, int value)
         ctx->replicas = value;
     }
     else if (k == "profile") ctx->profile = value;
+    else if (k == "no_fuse") ctx->no_fuse = value;   // 1: separate reduce/solve kernels even for small grids (A/B)
     else throw vm_error(VM_ERR_INVALID, "unknown tuning key: " + k);
     VM_API_END
 }

@@ -110,6 +110,81 @@ __device__ __forceinline__ void flush_grid(const double* __restrict__ grid, doub
 }
 
 
+// ------------------------------------------------ fused cross-CTA finish ----
+// The last CTA to finish (atomic ticket) sums all per-CTA rows in a fixed order and, on a single
+// GPU, also solves the periodic Poisson system -- the reduce and solve launches of a step disappear.
+// Used for n <= VM_FUSE_MAX_N; larger grids use the separate multi-CTA kernels.
+#define VM_FUSE_MAX_N 128
+enum { FINISH_NONE = 0, FINISH_REDUCE = 1, FINISH_REDUCE_SOLVE = 2 };
+
+struct FinishParams {
+    int mode;
+    unsigned* ticket;       // device counter, zero on entry, reset by the last CTA
+    double* rhs;            // n: reduced deposit
+    const double* G;        // n: circulant pseudo-inverse kernel      (FINISH_REDUCE_SOLVE)
+    double* phi;            // n
+    double* dcoef;          // n
+    double inv_h;
+};
+
+__device__ __forceinline__ void finish_last_cta(const FinishParams& F, const double* rows, int nrows, int n,
+                                                double* __restrict__ sm_a /* >= 3n doubles, free */,
+                                                double* __restrict__ scratch /* blockDim.x doubles */)
+{
+    __shared__ int s_last;
+    __threadfence();                                   // publish this CTA's row
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(F.ticket, 1u) == gridDim.x - 1u);
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const int T = blockDim.x, t = threadIdx.x;
+    int P = 1;
+    while (2 * P * n <= T && 2 * P <= nrows) P *= 2;
+    if (t < n * P) {
+        const int i = t % n, part = t / n;
+        double s = 0.0;
+        for (int r = part; r < nrows; r += P) s += __ldcg(rows + (size_t)r * n + i);
+        scratch[part * n + i] = s;
+    }
+    __syncthreads();
+    double* r_sh = sm_a;            // rhs - mean
+    double* phi_sh = sm_a + n;
+    if (t < n) {
+        double s = 0.0;
+        for (int part = 0; part < P; ++part) s += scratch[part * n + t];
+        F.rhs[t] = s;
+        r_sh[t] = s;
+    }
+    if (F.mode == FINISH_REDUCE_SOLVE) {
+        __syncthreads();
+        if (t < 32) {                // mean in a fixed order: strided lane sums, then the xor tree
+            double s = 0.0;
+            for (int j = t; j < n; j += 32) s += r_sh[j];
+            s = warp_sum(s);
+            if (t == 0) sm_a[2 * n] = s / (double)n;
+        }
+        __syncthreads();
+        const double mean = sm_a[2 * n];
+        __syncthreads();
+        if (t < n) r_sh[t] -= mean;
+        __syncthreads();
+        if (t < n) {
+            double a = 0.0;
+            int idx = t;             // G[(t - j) mod n]
+            for (int j = 0; j < n; ++j) {
+                a = fma(__ldg(F.G + idx), r_sh[j], a);
+                idx = (idx == 0) ? n - 1 : idx - 1;
+            }
+            phi_sh[t] = a;
+            F.phi[t] = a;
+        }
+        __syncthreads();
+        if (t < n) F.dcoef[t] = (phi_sh[t + 1 == n ? 0 : t + 1] - phi_sh[t]) * F.inv_h;
+    }
+    if (t == 0) *F.ticket = 0u;      // ready for the next launch on this stream
+}
+
 // ================================================================ host ======
 struct DepositPlan {
     int var, rep_log2, grid, threads;

@@ -44,13 +44,14 @@ struct vm_ctx {
     unsigned long long launches = 0;
     cudaEvent_t events[VM_MAX_EVENTS] = {};
     // tuning (0 = auto)
-    int ctas_per_sm = 0, threads_per_cta = 0, replicas = 0, profile = 0;
+    int ctas_per_sm = 0, threads_per_cta = 0, replicas = 0, profile = 0, no_fuse = 0;
     // per-launch event brackets of the dominant kernel (profile == 1)
     std::vector<cudaEvent_t> prof_events;   // pairs: [2i] start, [2i+1] stop
     size_t prof_used = 0;                    // events in use since the last read
     // communicator (one process per GPU)
     void* nccl_comm = nullptr;
     int rank = 0, nranks = 1;
+    unsigned* ticket = nullptr;          // device counter for the last-CTA finish (always zero between launches)
     // scratch: per-CTA partial rows for the fixed-order reductions
     double* partials = nullptr;
     size_t partials_elems = 0;

@@ -71,10 +71,12 @@ __device__ __forceinline__ void process(double& xp, double& vp, double wp, bool 
     scatter<K, VAR>(wg, n, P.rep_log2, rep, lane, b0, val, active);
 }
 
-template <int K, int VAR, int MODE>
+// U = pairs of particles each thread keeps in flight per iteration (software prefetch one iteration
+// ahead): the deposit-only pass moves just 16 B/particle and needs U = 2 to keep enough bytes in flight.
+template <int K, int VAR, int MODE, int U>
 __global__ void __launch_bounds__(1024, 1)
 k_vp_pass(double* __restrict__ x, double* __restrict__ v, const double* __restrict__ w,
-          const double* __restrict__ dcoef, double* __restrict__ out, const PassParams P)
+          const double* __restrict__ dcoef, double* __restrict__ out, const PassParams P, const FinishParams F)
 {
     extern __shared__ double smem[];
     const int n = P.map.n;
@@ -94,30 +96,42 @@ k_vp_pass(double* __restrict__ x, double* __restrict__ v, const double* __restri
     const long npairs = P.n >> 1;
     const long stride = (long)gridDim.x * blockDim.x;
     const long gtid = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long iters = (npairs + stride - 1) / stride;   // uniform trip count: the scatter is warp-collective
+    const long iters = (npairs + U * stride - 1) / (U * stride);   // uniform trip count: the scatter is warp-collective
 
-    double2 cx = make_double2(0., 0.), cv = cx, cw = cx, nx = cx, nv = cx, nw = cx;
-    if (gtid < npairs) {
-        cx = ld_stream2(x + 2 * gtid);
-        if (MODE != MODE_DEPOSIT) cv = ld_stream2(v + 2 * gtid);
-        cw = ld_stream2(w + 2 * gtid);
+    double2 cx[U], cv[U], cw[U], nx[U], nv[U], nw[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        cx[u] = cv[u] = cw[u] = nx[u] = nv[u] = nw[u] = make_double2(0., 0.);
+        const long q = u * stride + gtid;
+        if (q < npairs) {
+            cx[u] = ld_stream2(x + 2 * q);
+            if (MODE != MODE_DEPOSIT) cv[u] = ld_stream2(v + 2 * q);
+            cw[u] = ld_stream2(w + 2 * q);
+        }
     }
     for (long it = 0; it < iters; ++it) {
-        const long q = it * stride + gtid;
-        const long qn = q + stride;
-        const bool active = q < npairs;
-        if (qn < npairs) {                       // software prefetch of the next pair
-            nx = ld_stream2(x + 2 * qn);
-            if (MODE != MODE_DEPOSIT) nv = ld_stream2(v + 2 * qn);
-            nw = ld_stream2(w + 2 * qn);
+        const long base = it * U * stride + gtid;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {                // software prefetch of the next iteration's pairs
+            const long qn = base + (U + u) * stride;
+            if (qn < npairs) {
+                nx[u] = ld_stream2(x + 2 * qn);
+                if (MODE != MODE_DEPOSIT) nv[u] = ld_stream2(v + 2 * qn);
+                nw[u] = ld_stream2(w + 2 * qn);
+            }
         }
-        process<K, VAR, MODE>(cx.x, cv.x, cw.x, active, P, dsh, wg, rep, lane);
-        process<K, VAR, MODE>(cx.y, cv.y, cw.y, active, P, dsh, wg, rep, lane);
-        if (active && MODE != MODE_DEPOSIT) {
-            st_stream2(x + 2 * q, cx);
-            if (MODE == MODE_PUSH_DEPOSIT) st_stream2(v + 2 * q, cv);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long q = base + u * stride;
+            const bool active = q < npairs;
+            process<K, VAR, MODE>(cx[u].x, cv[u].x, cw[u].x, active, P, dsh, wg, rep, lane);
+            process<K, VAR, MODE>(cx[u].y, cv[u].y, cw[u].y, active, P, dsh, wg, rep, lane);
+            if (active && MODE != MODE_DEPOSIT) {
+                st_stream2(x + 2 * q, cx[u]);
+                if (MODE == MODE_PUSH_DEPOSIT) st_stream2(v + 2 * q, cv[u]);
+            }
+            cx[u] = nx[u]; cv[u] = nv[u]; cw[u] = nw[u];
         }
-        cx = nx; cv = nv; cw = nw;
     }
     if ((P.n & 1) && blockIdx.x == 0 && warp == 0) {   // odd particle count: last particle, lane 0 of one warp
         const bool active = (lane == 0);
@@ -134,9 +148,25 @@ k_vp_pass(double* __restrict__ x, double* __restrict__ v, const double* __restri
         }
     }
     flush_grid<VAR>(grid, scratch, out, n, P.rep_log2, nwarps, P.ncols);
+    if (VAR != VAR_ATOMIC && F.mode != FINISH_NONE) finish_last_cta(F, out, gridDim.x, n, grid, scratch);
 }
 
 // ------------------------------------------- kick + drift without deposit ---
+template <int K>
+__device__ __forceinline__ void push_one(double& xp, double& vp, const PassParams& P, const double* __restrict__ dsh)
+{
+    if (P.drift0 != 0.0) xp = __dadd_rn(xp, __dmul_rn(P.drift0, vp));
+    if (P.kick != 0.0) {
+        int b0;
+        double xi;
+        cell_of(P.map, xp, b0, xi);
+        const double dphi = gather_dphi<K>(dsh, P.map.n, b0, xi);
+        vp = __dadd_rn(vp, __dmul_rn(P.kick, dphi));
+        if (P.kick2 != 0.0) vp = __dadd_rn(vp, __dmul_rn(P.kick2, dphi));
+    }
+    if (P.drift1 != 0.0) xp = __dadd_rn(xp, __dmul_rn(P.drift1, vp));
+}
+
 template <int K>
 __global__ void __launch_bounds__(512, 2)
 k_vp_push(double* __restrict__ x, double* __restrict__ v, const double* __restrict__ w,
@@ -147,28 +177,47 @@ k_vp_push(double* __restrict__ x, double* __restrict__ v, const double* __restri
     double* dsh = smem;
     for (int i = threadIdx.x; i < n; i += blockDim.x) dsh[i] = dcoef[i];
     __syncthreads();
+    constexpr int U = 2;
+    const long npairs = P.n >> 1;
     const long stride = (long)gridDim.x * blockDim.x;
+    const long gtid = (long)blockIdx.x * blockDim.x + threadIdx.x;
     double s2 = 0.0, s1 = 0.0, s0 = 0.0;
-    for (long p = (long)blockIdx.x * blockDim.x + threadIdx.x; p < P.n; p += stride) {
-        double xp = ld_stream(x + p), vp = ld_stream(v + p);
-        if (P.drift0 != 0.0) xp = __dadd_rn(xp, __dmul_rn(P.drift0, vp));
-        if (P.kick != 0.0) {
-            int b0;
-            double xi;
-            cell_of(P.map, xp, b0, xi);
-            const double dphi = gather_dphi<K>(dsh, n, b0, xi);
-            vp = __dadd_rn(vp, __dmul_rn(P.kick, dphi));
-            if (P.kick2 != 0.0) vp = __dadd_rn(vp, __dmul_rn(P.kick2, dphi));
+    for (long base = gtid; base < npairs; base += U * stride) {
+        double2 cx[U], cv[U], cw[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long q = base + u * stride;
+            if (q < npairs) {
+                cx[u] = ld_stream2(x + 2 * q);
+                cv[u] = ld_stream2(v + 2 * q);
+                if (P.diag) cw[u] = ld_stream2(w + 2 * q);
+            }
         }
-        if (P.drift1 != 0.0) xp = __dadd_rn(xp, __dmul_rn(P.drift1, vp));
-        st_stream(x + p, xp);
-        st_stream(v + p, vp);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long q = base + u * stride;
+            if (q < npairs) {
+                push_one<K>(cx[u].x, cv[u].x, P, dsh);
+                push_one<K>(cx[u].y, cv[u].y, P, dsh);
+                st_stream2(x + 2 * q, cx[u]);
+                st_stream2(v + 2 * q, cv[u]);
+                if (P.diag) {
+                    const double a = cw[u].x * cv[u].x, b = cw[u].y * cv[u].y;
+                    s2 = fma(a, cv[u].x, s2); s2 = fma(b, cv[u].y, s2);
+                    s1 += a; s1 += b;
+                    s0 += cw[u].x; s0 += cw[u].y;
+                }
+            }
+        }
+    }
+    if ((P.n & 1) && gtid == 0) {
+        double xp = x[P.n - 1], vp = v[P.n - 1];
+        push_one<K>(xp, vp, P, dsh);
+        x[P.n - 1] = xp;
+        v[P.n - 1] = vp;
         if (P.diag) {
-            const double wp = ld_stream(w + p);
-            const double wv = wp * vp;
-            s2 = fma(wv, vp, s2);
-            s1 += wv;
-            s0 += wp;
+            const double wp = w[P.n - 1];
+            s2 = fma(wp * vp, vp, s2); s1 += wp * vp; s0 += wp;
         }
     }
     if (P.diag) {
@@ -254,39 +303,40 @@ namespace {
 
 template <int K, int VAR, int MODE>
 void launch_pass_inst(vm_ctx* ctx, const DepositPlan& pl, double* x, double* v, const double* w,
-                      const double* dcoef, double* out, const PassParams& P)
+                      const double* dcoef, double* out, const PassParams& P, const FinishParams& F)
 {
+    constexpr int U = (MODE == MODE_DEPOSIT) ? 2 : 1;
     static size_t configured[64] = {};   // per device: max dynamic smem already opted into for this instantiation
     size_t& conf = configured[ctx->device & 63];
     if (pl.smem > conf) {
-        VM_CUDA(cudaFuncSetAttribute(k_vp_pass<K, VAR, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+        VM_CUDA(cudaFuncSetAttribute(k_vp_pass<K, VAR, MODE, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
         conf = pl.smem;
     }
-    k_vp_pass<K, VAR, MODE><<<pl.grid, pl.threads, pl.smem, ctx->stream>>>(x, v, w, dcoef, out, P);
+    k_vp_pass<K, VAR, MODE, U><<<pl.grid, pl.threads, pl.smem, ctx->stream>>>(x, v, w, dcoef, out, P, F);
     VM_LAUNCHED(ctx);
 }
 
 template <int K, int MODE>
 void launch_pass_var(vm_ctx* ctx, const DepositPlan& pl, double* x, double* v, const double* w,
-                     const double* dcoef, double* out, const PassParams& P)
+                     const double* dcoef, double* out, const PassParams& P, const FinishParams& F)
 {
     switch (pl.var) {
-        case VAR_PRIV: launch_pass_inst<K, VAR_PRIV, MODE>(ctx, pl, x, v, w, dcoef, out, P); break;
-        case VAR_MATCH: launch_pass_inst<K, VAR_MATCH, MODE>(ctx, pl, x, v, w, dcoef, out, P); break;
-        default: launch_pass_inst<K, VAR_ATOMIC, MODE>(ctx, pl, x, v, w, dcoef, out, P); break;
+        case VAR_PRIV: launch_pass_inst<K, VAR_PRIV, MODE>(ctx, pl, x, v, w, dcoef, out, P, F); break;
+        case VAR_MATCH: launch_pass_inst<K, VAR_MATCH, MODE>(ctx, pl, x, v, w, dcoef, out, P, F); break;
+        default: launch_pass_inst<K, VAR_ATOMIC, MODE>(ctx, pl, x, v, w, dcoef, out, P, F); break;
     }
 }
 
 template <int MODE>
 void launch_pass(vm_ctx* ctx, int order, const DepositPlan& pl, double* x, double* v, const double* w,
-                 const double* dcoef, double* out, const PassParams& P)
+                 const double* dcoef, double* out, const PassParams& P, const FinishParams& F)
 {
     switch (order) {
-        case 2: launch_pass_var<2, MODE>(ctx, pl, x, v, w, dcoef, out, P); break;
-        case 3: launch_pass_var<3, MODE>(ctx, pl, x, v, w, dcoef, out, P); break;
-        case 4: launch_pass_var<4, MODE>(ctx, pl, x, v, w, dcoef, out, P); break;
-        case 5: launch_pass_var<5, MODE>(ctx, pl, x, v, w, dcoef, out, P); break;
-        case 6: launch_pass_var<6, MODE>(ctx, pl, x, v, w, dcoef, out, P); break;
+        case 2: launch_pass_var<2, MODE>(ctx, pl, x, v, w, dcoef, out, P, F); break;
+        case 3: launch_pass_var<3, MODE>(ctx, pl, x, v, w, dcoef, out, P, F); break;
+        case 4: launch_pass_var<4, MODE>(ctx, pl, x, v, w, dcoef, out, P, F); break;
+        case 5: launch_pass_var<5, MODE>(ctx, pl, x, v, w, dcoef, out, P, F); break;
+        case 6: launch_pass_var<6, MODE>(ctx, pl, x, v, w, dcoef, out, P, F); break;
         default: throw vm_error(VM_ERR_UNSUPPORTED, "spline order must be in 2..6");
     }
 }
@@ -350,8 +400,10 @@ void vm_gather_dev(vm_field* f, const double* x_dev, long np, double* e_dev, dou
 }
 
 // One particle pass with deposition; leaves the LOCAL (this rank's) deposit in f->rhs[0..n).
+// want_solve: also produce phi/dcoef (all-reduce + replicated solve); on a single GPU with a small
+// grid both the reduction and the solve are fused into the pass kernel's last CTA.
 static void pass_with_deposit(vm_field* f, vm_particles* p, int pass_mode, int deposit_mode, PassParams P,
-                              bool prof_deposit = false)
+                              bool want_solve, bool prof_deposit = false)
 {
     vm_ctx* ctx = f->ctx;
     const int n = f->n;
@@ -361,23 +413,32 @@ static void pass_with_deposit(vm_field* f, vm_particles* p, int pass_mode, int d
     P.n = p->n;
     P.rep_log2 = pl.rep_log2;
     P.ncols = ncols;
+    FinishParams F{};
+    F.mode = FINISH_NONE;
     double* out;
     if (pl.var == VAR_ATOMIC) {
         VM_CUDA(cudaMemsetAsync(f->rhs, 0, (size_t)ncols * sizeof(double), ctx->stream));
         out = f->rhs;
     } else {
         out = vm_partials(ctx, (size_t)pl.grid * ncols);
+        const size_t gdoubles = ((size_t)n << pl.rep_log2) * (size_t)(pl.threads / 32);
+        if (n <= VM_FUSE_MAX_N && !ctx->no_fuse && gdoubles >= (size_t)2 * n + 1) {
+            F.mode = (want_solve && ctx->nranks == 1) ? FINISH_REDUCE_SOLVE : FINISH_REDUCE;
+            F.ticket = ctx->ticket;
+            F.rhs = f->rhs; F.G = f->G; F.phi = f->phi; F.dcoef = f->dcoef; F.inv_h = f->map.inv_h;
+        }
     }
     // the dominant kernel of its caller: the fused pass inside vm_vp_run, the deposit pass elsewhere
     const bool prof = (pass_mode == MODE_PUSH_DEPOSIT) || (pass_mode == MODE_DEPOSIT && prof_deposit);
     if (prof) vm_prof_mark(ctx);
     switch (pass_mode) {
-        case MODE_DEPOSIT: launch_pass<MODE_DEPOSIT>(ctx, f->order, pl, p->x, p->v, p->w, f->dcoef, out, P); break;
-        case MODE_PUSH_DEPOSIT: launch_pass<MODE_PUSH_DEPOSIT>(ctx, f->order, pl, p->x, p->v, p->w, f->dcoef, out, P); break;
-        default: launch_pass<MODE_DRIFT_DEPOSIT>(ctx, f->order, pl, p->x, p->v, p->w, f->dcoef, out, P); break;
+        case MODE_DEPOSIT: launch_pass<MODE_DEPOSIT>(ctx, f->order, pl, p->x, p->v, p->w, f->dcoef, out, P, F); break;
+        case MODE_PUSH_DEPOSIT: launch_pass<MODE_PUSH_DEPOSIT>(ctx, f->order, pl, p->x, p->v, p->w, f->dcoef, out, P, F); break;
+        default: launch_pass<MODE_DRIFT_DEPOSIT>(ctx, f->order, pl, p->x, p->v, p->w, f->dcoef, out, P, F); break;
     }
     if (prof) vm_prof_mark(ctx);
-    if (pl.var != VAR_ATOMIC) vm_field_reduce_rows(f, out, pl.grid, ncols, f->rhs);
+    if (pl.var != VAR_ATOMIC && F.mode == FINISH_NONE) vm_field_reduce_rows(f, out, pl.grid, ncols, f->rhs);
+    if (want_solve && F.mode != FINISH_REDUCE_SOLVE) vm_field_solve_local(f, true);
 }
 
 static void wv_moments(vm_field* f, vm_particles* p)
@@ -407,7 +468,7 @@ int vm_deposit(vm_field* f, vm_particles* p, int mode)
     check_pair(f, p, "vm_deposit");
     VM_REQUIRE(mode == VM_DEPOSIT_DETERMINISTIC || mode == VM_DEPOSIT_ATOMIC, "vm_deposit: unknown mode");
     PassParams P{};
-    pass_with_deposit(f, p, MODE_DEPOSIT, mode, P, true);
+    pass_with_deposit(f, p, MODE_DEPOSIT, mode, P, false, true);
     VM_API_END
 }
 
@@ -478,8 +539,7 @@ int vm_diagnostics(vm_field* f, vm_particles* p, double chi, double* out4)
     VM_REQUIRE(out4 != nullptr && chi != 0.0, "vm_diagnostics: bad argument");
     vm_ctx* ctx = f->ctx;
     PassParams P{};
-    pass_with_deposit(f, p, MODE_DEPOSIT, VM_DEPOSIT_DETERMINISTIC, P);
-    vm_field_solve_local(f, true);
+    pass_with_deposit(f, p, MODE_DEPOSIT, VM_DEPOSIT_DETERMINISTIC, P, true);
     vm_field_energy_dev(f);
     wv_moments(f, p);
     double* rows = vm_field_diag_rows(f, 1);
@@ -518,8 +578,7 @@ int vm_vp_run(vm_field* f, vm_particles* p, double dt, int nsteps, int diag_ever
         // W needs phi at the current (integer-time) positions: update!(efield, x, w, t) + save_timestep!
         if (!frozen) {
             PassParams D{};
-            pass_with_deposit(f, p, MODE_DEPOSIT, dmode, D);
-            vm_field_solve_local(f, true);
+            pass_with_deposit(f, p, MODE_DEPOSIT, dmode, D, true);
         }
         vm_field_energy_dev(f);
         if (!have_wv) wv_moments(f, p);
@@ -550,13 +609,12 @@ int vm_vp_run(vm_field* f, vm_particles* p, double dt, int nsteps, int diag_ever
                 k_drift<<<grid, threads, 0, ctx->stream>>>(p->x, p->v, p->n, hd);
                 VM_LAUNCHED(ctx);
                 PassParams D{};
-                pass_with_deposit(f, p, MODE_DEPOSIT, dmode, D);
+                pass_with_deposit(f, p, MODE_DEPOSIT, dmode, D, true);
             } else {
                 PassParams P{};
                 P.drift1 = hd;
-                pass_with_deposit(f, p, MODE_DRIFT_DEPOSIT, dmode, P);
+                pass_with_deposit(f, p, MODE_DRIFT_DEPOSIT, dmode, P, true);
             }
-            vm_field_solve_local(f, true);
             staggered = true;
         }
         if (is_diag || last || unfused) {
@@ -574,8 +632,7 @@ int vm_vp_run(vm_field* f, vm_particles* p, double dt, int nsteps, int diag_ever
         } else {
             PassParams P{};
             P.kick = k1; P.kick2 = k2; P.drift1 = hd; P.drift2 = hd;
-            pass_with_deposit(f, p, MODE_PUSH_DEPOSIT, dmode, P);
-            vm_field_solve_local(f, true);
+            pass_with_deposit(f, p, MODE_PUSH_DEPOSIT, dmode, P, true);
         }
     }
     if (nrows > 0) {

@@ -67,7 +67,8 @@ __device__ __forceinline__ void vdeposit_one(double vp, double wp, bool active, 
 template <int K, int VAR>
 __global__ void __launch_bounds__(1024, 1)
 k_v_deposit(const double* __restrict__ v, const double* __restrict__ w, long np, VCell m,
-            const double* __restrict__ cellpoly, int npar, int rep_log2, double* __restrict__ out)
+            const double* __restrict__ cellpoly, int npar, int rep_log2, double* __restrict__ out,
+            const FinishParams F)
 {
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -80,19 +81,32 @@ k_v_deposit(const double* __restrict__ v, const double* __restrict__ w, long np,
     double* wg = (VAR == VAR_ATOMIC) ? grid : grid + warp * gsz;
     const int rep = ((VAR == VAR_ATOMIC) ? warp : lane) & ((1 << rep_log2) - 1);
 
+    constexpr int U = 2;          // pairs in flight per thread (16 B/particle pass: see k_vp_pass)
     const long npairs = np >> 1;
     const long stride = (long)gridDim.x * blockDim.x;
     const long gtid = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long iters = (npairs + stride - 1) / stride;
-    double2 cv = make_double2(0., 0.), cw = cv, nv = cv, nw = cv;
-    if (gtid < npairs) { cv = ld_stream2(v + 2 * gtid); cw = ld_stream2(w + 2 * gtid); }
+    const long iters = (npairs + U * stride - 1) / (U * stride);
+    double2 cv[U], cw[U], nv[U], nw[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        cv[u] = cw[u] = nv[u] = nw[u] = make_double2(0., 0.);
+        const long q = u * stride + gtid;
+        if (q < npairs) { cv[u] = ld_stream2(v + 2 * q); cw[u] = ld_stream2(w + 2 * q); }
+    }
     for (long it = 0; it < iters; ++it) {
-        const long q = it * stride + gtid, qn = q + stride;
-        const bool active = q < npairs;
-        if (qn < npairs) { nv = ld_stream2(v + 2 * qn); nw = ld_stream2(w + 2 * qn); }
-        vdeposit_one<K, VAR>(cv.x, cw.x, active, m, cellpoly, wg, npar, rep_log2, rep, lane);
-        vdeposit_one<K, VAR>(cv.y, cw.y, active, m, cellpoly, wg, npar, rep_log2, rep, lane);
-        cv = nv; cw = nw;
+        const long base = it * U * stride + gtid;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long qn = base + (U + u) * stride;
+            if (qn < npairs) { nv[u] = ld_stream2(v + 2 * qn); nw[u] = ld_stream2(w + 2 * qn); }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const bool active = (base + u * stride) < npairs;
+            vdeposit_one<K, VAR>(cv[u].x, cw[u].x, active, m, cellpoly, wg, npar, rep_log2, rep, lane);
+            vdeposit_one<K, VAR>(cv[u].y, cw[u].y, active, m, cellpoly, wg, npar, rep_log2, rep, lane);
+            cv[u] = nv[u]; cw[u] = nw[u];
+        }
     }
     if ((np & 1) && blockIdx.x == 0 && warp == 0) {
         const bool active = (lane == 0);
@@ -100,6 +114,7 @@ k_v_deposit(const double* __restrict__ v, const double* __restrict__ w, long np,
                              rep_log2, rep, lane);
     }
     flush_grid<VAR>(grid, scratch, out, npar, rep_log2, nwarps, npar);
+    if (VAR != VAR_ATOMIC && F.mode != FINISH_NONE) finish_last_cta(F, out, gridDim.x, npar, grid, scratch);
 }
 
 // ------------------------------------------------------------- small solves -
@@ -322,7 +337,8 @@ void geometry(vm_ctx* ctx, int* grid, int* threads)
 }
 
 template <int K, int VAR>
-void launch_vdep_inst(vm_vspline* s, const DepositPlan& pl, const double* v, const double* w, long np, double* out)
+void launch_vdep_inst(vm_vspline* s, const DepositPlan& pl, const double* v, const double* w, long np, double* out,
+                      const FinishParams& F)
 {
     vm_ctx* ctx = s->ctx;
     static size_t configured[64] = {};
@@ -332,17 +348,18 @@ void launch_vdep_inst(vm_vspline* s, const DepositPlan& pl, const double* v, con
         conf = pl.smem;
     }
     k_v_deposit<K, VAR><<<pl.grid, pl.threads, pl.smem, ctx->stream>>>(v, w, np, vcell(s), s->cellpoly, s->npar,
-                                                                      pl.rep_log2, out);
+                                                                      pl.rep_log2, out, F);
     VM_LAUNCHED(ctx);
 }
 
 template <int K>
-void launch_vdep_var(vm_vspline* s, const DepositPlan& pl, const double* v, const double* w, long np, double* out)
+void launch_vdep_var(vm_vspline* s, const DepositPlan& pl, const double* v, const double* w, long np, double* out,
+                     const FinishParams& F)
 {
     switch (pl.var) {
-        case VAR_PRIV: launch_vdep_inst<K, VAR_PRIV>(s, pl, v, w, np, out); break;
-        case VAR_MATCH: launch_vdep_inst<K, VAR_MATCH>(s, pl, v, w, np, out); break;
-        default: launch_vdep_inst<K, VAR_ATOMIC>(s, pl, v, w, np, out); break;
+        case VAR_PRIV: launch_vdep_inst<K, VAR_PRIV>(s, pl, v, w, np, out, F); break;
+        case VAR_MATCH: launch_vdep_inst<K, VAR_MATCH>(s, pl, v, w, np, out, F); break;
+        default: launch_vdep_inst<K, VAR_ATOMIC>(s, pl, v, w, np, out, F); break;
     }
 }
 
@@ -362,10 +379,17 @@ void project_dev(vm_vspline* s, const double* v, const double* w, long np)
     vm_ctx* ctx = s->ctx;
     DepositPlan pl = plan_deposit(ctx, s->npar, false, VM_DEPOSIT_DETERMINISTIC);
     double* out = vm_partials(ctx, (size_t)pl.grid * s->npar);
+    FinishParams F{};
+    const size_t gdoubles = ((size_t)s->npar << pl.rep_log2) * (size_t)(pl.threads / 32);
+    if (s->npar <= VM_FUSE_MAX_N && !ctx->no_fuse && pl.var != VAR_ATOMIC && gdoubles >= (size_t)2 * s->npar + 1) {
+        F.mode = FINISH_REDUCE;           // last CTA sums the per-CTA rows in a fixed order
+        F.ticket = ctx->ticket;
+        F.rhs = s->rhs;
+    }
     vm_prof_mark(ctx);
-    VM_ORDER_SWITCH(s->order, launch_vdep_var<K>(s, pl, v, w, np, out));
+    VM_ORDER_SWITCH(s->order, launch_vdep_var<K>(s, pl, v, w, np, out, F));
     vm_prof_mark(ctx);
-    vm_reduce_rows(ctx, out, pl.grid, s->npar, s->rhs);
+    if (F.mode == FINISH_NONE) vm_reduce_rows(ctx, out, pl.grid, s->npar, s->rhs);
     vm_allreduce_sum(ctx, s->rhs, (size_t)s->npar);
     const int off = s->bc ? 1 : 0;
     k_v_solve<<<(s->nv + 7) / 8, 256, 0, ctx->stream>>>(s->minv, s->rhs, s->nv, off, s->npar, s->coef);
