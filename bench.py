@@ -197,6 +197,8 @@ def run_gpu(args):
     if world > 1:
         dist.init_process_group(backend="gloo")      # host-side rendezvous/barrier only
     ctx = vm.init_distributed_context(local)
+    if args.no_fuse:
+        ctx.set_tuning("no_fuse", 1)
     ntot = args.particles
     lo, hi = vm.shard_bounds(ntot, rank, world)
     nloc = hi - lo
@@ -327,6 +329,7 @@ def main():
     ap.add_argument("--particles", type=int, default=N_TOTAL)
     ap.add_argument("--atomic", action="store_true", help="use the shared-atomic deposit variant (A/B)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-fuse", action="store_true", help="separate reduce/solve kernels instead of the last-CTA finish (A/B)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

@@ -11,19 +11,20 @@
 enum { VAR_PRIV = 0, VAR_MATCH = 1, VAR_ATOMIC = 2 };
 
 // ---------------------------------------------------------------- scatter ---
-// Add val[j] to basis index (b0 + j) mod n, j < K, in this warp's replica grid.
+// Replica grids carry `ghost` extra rows after the n real ones, so a particle's K consecutive
+// basis indices b0 .. b0+K-1 never wrap inside the hot loop (periodic grids: ghost = K-1, folded back
+// onto rows 0..K-2 when the grid is flushed; clamped v-space grids: ghost = 0).
+//
+// Add val[j] to row b0 + j, j < K, in this warp's replica grid.  Inactive lanes must carry val == 0.
 template <int K, int VAR>
-__device__ __forceinline__ void scatter(double* __restrict__ wg, int n, int rep_log2, int rep, int lane,
+__device__ __forceinline__ void scatter(double* __restrict__ wg, int rep_log2, int rep, int lane,
                                         int b0, const double (&val)[K], bool active)
 {
     if (VAR == VAR_PRIV) {
-        if (active) {
+        // one private column per lane: no collisions, no branches, immediate-offset LDS/DADD/STS
+        double* a = wg + (b0 << 5) + lane;
 #pragma unroll
-            for (int j = 0; j < K; ++j) {
-                double* a = wg + (wrap_add(b0, j, n) << 5) + lane;
-                *a += val[j];
-            }
-        }
+        for (int j = 0; j < K; ++j) a[j * 32] += val[j];
         return;
     }
     // group the lanes that target the same (cell, replica): in-warp sort-by-cell
@@ -45,70 +46,66 @@ __device__ __forceinline__ void scatter(double* __restrict__ wg, int n, int rep_
         }
         todo &= todo - 1u;
     }
+    double* a = wg + (b0 << rep_log2) + rep;
     if (VAR == VAR_MATCH) {
 #pragma unroll
         for (int j = 0; j < K; ++j) {
-            if (is_leader && active) {
-                double* a = wg + (wrap_add(b0, j, n) << rep_log2) + rep;
-                *a += acc[j];
-            }
+            if (is_leader && active) a[j << rep_log2] += acc[j];
             __syncwarp();
         }
     } else {  // VAR_ATOMIC: one warp-aggregated shared atomic per distinct cell
         if (is_leader && active) {
 #pragma unroll
-            for (int j = 0; j < K; ++j) atomicAdd(wg + (wrap_add(b0, j, n) << rep_log2) + rep, acc[j]);
+            for (int j = 0; j < K; ++j) atomicAdd(a + (j << rep_log2), acc[j]);
         }
     }
 }
 
-// Sum all replica copies of every basis index in a fixed order and emit the CTA's partial row.
+// Sum all replica copies of every row in a fixed order (ghost rows folded onto rows 0..ghost-1) and
+// emit the CTA's partial row.
 template <int VAR>
 __device__ __forceinline__ void flush_grid(const double* __restrict__ grid, double* __restrict__ scratch,
-                                           double* __restrict__ out, int n, int rep_log2, int nwarps, int ncols)
+                                           double* __restrict__ out, int n, int ghost, int rep_log2, int nwarps,
+                                           int ncols)
 {
     const int T = blockDim.x;
-    const int gsz = n << rep_log2;
+    const int gsz = (n + ghost) << rep_log2;
     const int ncopies = (VAR == VAR_ATOMIC) ? (1 << rep_log2) : (nwarps << rep_log2);
     const int R = 1 << rep_log2;
     __syncthreads();
     int P = 1;
     while (2 * P * n <= T && 2 * P <= ncopies) P *= 2;   // P partial sums per index
-    for (int base = 0; base < n; base += T) {           // (only one trip when n <= T)
+    auto row_sum = [&](int i, int c0, int cstep) {
+        double s = 0.0;
+        for (int c = c0; c < ncopies; c += cstep) {
+            const int wq = c >> rep_log2, r = c & (R - 1);
+            s += grid[(VAR == VAR_ATOMIC ? 0 : wq * gsz) + (i << rep_log2) + r];
+        }
+        if (i < ghost)
+            for (int c = c0; c < ncopies; c += cstep) {
+                const int wq = c >> rep_log2, r = c & (R - 1);
+                s += grid[(VAR == VAR_ATOMIC ? 0 : wq * gsz) + ((n + i) << rep_log2) + r];
+            }
+        return s;
+    };
+    if (P > 1) {                                         // n * P <= T: one trip
         const int t = threadIdx.x;
-        if (P > 1) {
-            if (t < n * P) {
-                const int i = t % n, part = t / n;
-                double s = 0.0;
-                for (int c = part; c < ncopies; c += P) {
-                    const int wq = c >> rep_log2, r = c & (R - 1);
-                    s += grid[(VAR == VAR_ATOMIC ? 0 : wq * gsz) + (i << rep_log2) + r];
-                }
-                scratch[part * n + i] = s;
-            }
-            __syncthreads();
-            if (t < n) {
-                double s = 0.0;
-                for (int part = 0; part < P; ++part) s += scratch[part * n + t];
-                if (VAR == VAR_ATOMIC) atomicAdd(out + t, s);
-                else out[(size_t)blockIdx.x * ncols + t] = s;
-            }
-        } else {
-            const int i = base + t;
-            if (i < n) {
-                double s = 0.0;
-                for (int c = 0; c < ncopies; ++c) {
-                    const int wq = c >> rep_log2, r = c & (R - 1);
-                    s += grid[(VAR == VAR_ATOMIC ? 0 : wq * gsz) + (i << rep_log2) + r];
-                }
-                if (VAR == VAR_ATOMIC) atomicAdd(out + i, s);
-                else out[(size_t)blockIdx.x * ncols + i] = s;
-            }
+        if (t < n * P) scratch[(t / n) * n + (t % n)] = row_sum(t % n, t / n, P);
+        __syncthreads();
+        if (t < n) {
+            double s = 0.0;
+            for (int part = 0; part < P; ++part) s += scratch[part * n + t];
+            if (VAR == VAR_ATOMIC) atomicAdd(out + t, s);
+            else out[(size_t)blockIdx.x * ncols + t] = s;
+        }
+    } else {
+        for (int i = threadIdx.x; i < n; i += T) {
+            const double s = row_sum(i, 0, 1);
+            if (VAR == VAR_ATOMIC) atomicAdd(out + i, s);
+            else out[(size_t)blockIdx.x * ncols + i] = s;
         }
     }
-    if (VAR != VAR_ATOMIC && threadIdx.x < ncols - n) out[(size_t)blockIdx.x * ncols + n + threadIdx.x] = 0.0;
 }
-
 
 // ------------------------------------------------ fused cross-CTA finish ----
 // The last CTA to finish (atomic ticket) sums all per-CTA rows in a fixed order and, on a single
@@ -192,9 +189,10 @@ struct DepositPlan {
 };
 
 // Choose CTA shape + replica count so that the replica grids fit in shared memory.
-inline DepositPlan plan_deposit(vm_ctx* ctx, int n, bool with_dcoef, int mode)
+inline DepositPlan plan_deposit(vm_ctx* ctx, int n_real, int ghost, int extra_doubles, int mode)
 {
     const int sm = ctx->sm_count;
+    const int n = n_real + ghost;   // rows per replica grid
     struct Try { int ctas, threads; };
     std::vector<Try> tries;
     if (ctx->ctas_per_sm > 0 || ctx->threads_per_cta > 0) {
@@ -207,7 +205,7 @@ inline DepositPlan plan_deposit(vm_ctx* ctx, int n, bool with_dcoef, int mode)
         const int nwarps = t.threads / 32;
         size_t budget = sm_total / t.ctas - 1024;            // 1 KB per-CTA system reservation
         if (budget > ctx->smem_optin) budget = ctx->smem_optin;
-        const size_t fixed = ((with_dcoef ? (size_t)n : 0) + (size_t)t.threads) * sizeof(double);
+        const size_t fixed = ((size_t)extra_doubles + (size_t)t.threads) * sizeof(double);
         if (budget <= fixed) continue;
         const size_t avail = (budget - fixed) / sizeof(double);
         DepositPlan pl{};

@@ -165,16 +165,23 @@ __device__ __forceinline__ void bspline_uniform(double xi, double (&N)[K])
     }
 }
 
+// (x - a)/h -> (cell index mod n incl. the index rotation, fractional coordinate in [0,1)).
+// floor() without the slow fp64<->int conversion pipe: adding 1.5*2^52 leaves round-to-nearest(t) in
+// the low mantissa word; one compare turns the rounding into a floor.  Valid for |t| < 2^30.
 __device__ __forceinline__ void cell_of(const CellMap& m, double x, int& base, double& xi)
 {
     const double t = fma(x, m.inv_h, m.off);
-    const double fl = floor(t);
-    xi = t - fl;
-    const unsigned u = (unsigned)(__double2int_rd(t) + m.bias);   // in [0, 2^31)
+    const double big = 6755399441055744.0;             // 1.5 * 2^52
+    const double tm = t + big;
+    double r = tm - big;                                // round-to-nearest-even(t), exact
+    int c = __double2loint(tm);
+    if (r > t) { r -= 1.0; c -= 1; }
+    xi = t - r;
+    const unsigned u = (unsigned)(c + m.bias);          // in [0, 2^31)
     const unsigned q = __umulhi(u, m.inv_n);
-    unsigned r = u - q * (unsigned)m.n;
-    if (r >= (unsigned)m.n) r -= (unsigned)m.n;
-    base = (int)r;
+    unsigned rr = u - q * (unsigned)m.n;
+    if (rr >= (unsigned)m.n) rr -= (unsigned)m.n;
+    base = (int)min(rr, (unsigned)m.n - 1u);             // in-bounds even for garbage positions (|t| >= 2^30)
 }
 
 __device__ __forceinline__ int wrap_add(int i, int j, int n)

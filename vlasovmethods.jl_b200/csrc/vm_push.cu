@@ -32,16 +32,24 @@ struct PassParams {
 };
 
 // ---------------------------------------------------------------- gather ----
+// dsh is the derivative-coefficient vector D extended periodically by K-2 entries (dsh[n+i] = D[i]),
+// so the K-1 reads at b0 .. b0+K-2 need no index wrap.
 template <int K>
-__device__ __forceinline__ double gather_dphi(const double* __restrict__ dsh, int n, int b0, double xi)
+__device__ __forceinline__ double gather_dphi(const double* __restrict__ dsh, int b0, double xi)
 {
     // phi'(x) = sum_{j<K-1} N^{K-1}_j(xi) * D[(b0 + j) mod n],  D_m = (phi_{m+1} - phi_m) / h
     double Nd[K - 1 > 0 ? K - 1 : 1];
     bspline_uniform<(K - 1 > 0 ? K - 1 : 1)>(xi, Nd);
+    const double* d = dsh + b0;
     double s = 0.0;
 #pragma unroll
-    for (int j = 0; j < K - 1; ++j) s = fma(Nd[j], dsh[wrap_add(b0, j, n)], s);
+    for (int j = 0; j < K - 1; ++j) s = fma(Nd[j], d[j], s);
     return s;
+}
+
+__device__ __forceinline__ void load_dcoef_ext(double* __restrict__ dsh, const double* __restrict__ dcoef, int n, int ext)
+{
+    for (int i = threadIdx.x; i < n + ext; i += blockDim.x) dsh[i] = dcoef[i < n ? i : i - n];
 }
 
 // --------------------------------------------------------- the fused pass ---
@@ -49,12 +57,11 @@ template <int K, int VAR, int MODE>
 __device__ __forceinline__ void process(double& xp, double& vp, double wp, bool active, const PassParams& P,
                                         const double* __restrict__ dsh, double* __restrict__ wg, int rep, int lane)
 {
-    const int n = P.map.n;
     int b0;
     double xi;
     if (MODE == MODE_PUSH_DEPOSIT) {
         cell_of(P.map, xp, b0, xi);
-        const double dphi = gather_dphi<K>(dsh, n, b0, xi);
+        const double dphi = gather_dphi<K>(dsh, b0, xi);
         // literal (unfused) update order of s_acceleration!: v = v - dt * phi'
         vp = __dadd_rn(vp, __dmul_rn(P.kick, dphi));
         if (P.kick2 != 0.0) vp = __dadd_rn(vp, __dmul_rn(P.kick2, dphi));
@@ -67,12 +74,18 @@ __device__ __forceinline__ void process(double& xp, double& vp, double wp, bool 
     double val[K];
     bspline_uniform<K>(xi, val);
 #pragma unroll
-    for (int j = 0; j < K; ++j) val[j] *= wp;
-    scatter<K, VAR>(wg, n, P.rep_log2, rep, lane, b0, val, active);
+    for (int j = 0; j < K; ++j) val[j] *= wp;      // inactive lanes carry wp == 0
+    scatter<K, VAR>(wg, P.rep_log2, rep, lane, b0, val, active);
 }
 
-// U = pairs of particles each thread keeps in flight per iteration (software prefetch one iteration
-// ahead): the deposit-only pass moves just 16 B/particle and needs U = 2 to keep enough bytes in flight.
+template <int MODE>
+struct PairBuf {
+    double2 x, v, w;
+};
+
+// U = pairs of particles each thread keeps in flight per half-iteration.  The loop is unrolled twice
+// over two register buffer sets (A is processed while B is in flight and vice versa): no register
+// rotation, loads one half-iteration ahead.
 template <int K, int VAR, int MODE, int U>
 __global__ void __launch_bounds__(1024, 1)
 k_vp_pass(double* __restrict__ x, double* __restrict__ v, const double* __restrict__ w,
@@ -80,15 +93,15 @@ k_vp_pass(double* __restrict__ x, double* __restrict__ v, const double* __restri
 {
     extern __shared__ double smem[];
     const int n = P.map.n;
+    constexpr int GHOST = K - 1;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     double* dsh = smem;
-    double* grid = smem + (MODE == MODE_PUSH_DEPOSIT ? n : 0);
-    const int gsz = n << P.rep_log2;
+    double* grid = smem + (MODE == MODE_PUSH_DEPOSIT ? n + K : 0);
+    const int gsz = (n + GHOST) << P.rep_log2;
     const int gtotal = (VAR == VAR_ATOMIC) ? gsz : gsz * nwarps;
     double* scratch = grid + gtotal;
     for (int i = threadIdx.x; i < gtotal; i += blockDim.x) grid[i] = 0.0;
-    if (MODE == MODE_PUSH_DEPOSIT)
-        for (int i = threadIdx.x; i < n; i += blockDim.x) dsh[i] = dcoef[i];
+    if (MODE == MODE_PUSH_DEPOSIT) load_dcoef_ext(dsh, dcoef, n, K - 2 > 0 ? K - 2 : 0);
     __syncthreads();
     double* wg = (VAR == VAR_ATOMIC) ? grid : grid + warp * gsz;
     const int rep = ((VAR == VAR_ATOMIC) ? warp : lane) & ((1 << P.rep_log2) - 1);
@@ -98,40 +111,40 @@ k_vp_pass(double* __restrict__ x, double* __restrict__ v, const double* __restri
     const long gtid = (long)blockIdx.x * blockDim.x + threadIdx.x;
     const long iters = (npairs + U * stride - 1) / (U * stride);   // uniform trip count: the scatter is warp-collective
 
-    double2 cx[U], cv[U], cw[U], nx[U], nv[U], nw[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-        cx[u] = cv[u] = cw[u] = nx[u] = nv[u] = nw[u] = make_double2(0., 0.);
-        const long q = u * stride + gtid;
-        if (q < npairs) {
-            cx[u] = ld_stream2(x + 2 * q);
-            if (MODE != MODE_DEPOSIT) cv[u] = ld_stream2(v + 2 * q);
-            cw[u] = ld_stream2(w + 2 * q);
-        }
-    }
-    for (long it = 0; it < iters; ++it) {
-        const long base = it * U * stride + gtid;
-#pragma unroll
-        for (int u = 0; u < U; ++u) {                // software prefetch of the next iteration's pairs
-            const long qn = base + (U + u) * stride;
-            if (qn < npairs) {
-                nx[u] = ld_stream2(x + 2 * qn);
-                if (MODE != MODE_DEPOSIT) nv[u] = ld_stream2(v + 2 * qn);
-                nw[u] = ld_stream2(w + 2 * qn);
-            }
-        }
+    PairBuf<MODE> A[U], B[U];
+    auto load = [&](PairBuf<MODE> (&buf)[U], long it) {
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const long q = base + u * stride;
-            const bool active = q < npairs;
-            process<K, VAR, MODE>(cx[u].x, cv[u].x, cw[u].x, active, P, dsh, wg, rep, lane);
-            process<K, VAR, MODE>(cx[u].y, cv[u].y, cw[u].y, active, P, dsh, wg, rep, lane);
-            if (active && MODE != MODE_DEPOSIT) {
-                st_stream2(x + 2 * q, cx[u]);
-                if (MODE == MODE_PUSH_DEPOSIT) st_stream2(v + 2 * q, cv[u]);
+            const long q = (it * U + u) * stride + gtid;
+            buf[u].w = make_double2(0., 0.);            // out-of-range pairs deposit nothing
+            if (q < npairs) {
+                buf[u].x = ld_stream2(x + 2 * q);
+                if (MODE != MODE_DEPOSIT) buf[u].v = ld_stream2(v + 2 * q);
+                buf[u].w = ld_stream2(w + 2 * q);
             }
-            cx[u] = nx[u]; cv[u] = nv[u]; cw[u] = nw[u];
         }
+    };
+    auto work = [&](PairBuf<MODE> (&buf)[U], long it) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long q = (it * U + u) * stride + gtid;
+            const bool active = q < npairs;
+            process<K, VAR, MODE>(buf[u].x.x, buf[u].v.x, buf[u].w.x, active, P, dsh, wg, rep, lane);
+            process<K, VAR, MODE>(buf[u].x.y, buf[u].v.y, buf[u].w.y, active, P, dsh, wg, rep, lane);
+            if (active && MODE != MODE_DEPOSIT) {
+                st_stream2(x + 2 * q, buf[u].x);
+                if (MODE == MODE_PUSH_DEPOSIT) st_stream2(v + 2 * q, buf[u].v);
+            }
+        }
+    };
+#pragma unroll
+    for (int u = 0; u < U; ++u) A[u].x = A[u].v = B[u].x = B[u].v = make_double2(0., 0.);
+    load(A, 0);
+    for (long it = 0; it < iters; it += 2) {
+        load(B, it + 1);
+        work(A, it);
+        load(A, it + 2);
+        work(B, it + 1);        // all-inactive when iters is odd (costs one idle half-iteration)
     }
     if ((P.n & 1) && blockIdx.x == 0 && warp == 0) {   // odd particle count: last particle, lane 0 of one warp
         const bool active = (lane == 0);
@@ -147,7 +160,7 @@ k_vp_pass(double* __restrict__ x, double* __restrict__ v, const double* __restri
             if (MODE == MODE_PUSH_DEPOSIT) v[P.n - 1] = vp;
         }
     }
-    flush_grid<VAR>(grid, scratch, out, n, P.rep_log2, nwarps, P.ncols);
+    flush_grid<VAR>(grid, scratch, out, n, GHOST, P.rep_log2, nwarps, P.ncols);
     if (VAR != VAR_ATOMIC && F.mode != FINISH_NONE) finish_last_cta(F, out, gridDim.x, n, grid, scratch);
 }
 
@@ -160,7 +173,7 @@ __device__ __forceinline__ void push_one(double& xp, double& vp, const PassParam
         int b0;
         double xi;
         cell_of(P.map, xp, b0, xi);
-        const double dphi = gather_dphi<K>(dsh, P.map.n, b0, xi);
+        const double dphi = gather_dphi<K>(dsh, b0, xi);
         vp = __dadd_rn(vp, __dmul_rn(P.kick, dphi));
         if (P.kick2 != 0.0) vp = __dadd_rn(vp, __dmul_rn(P.kick2, dphi));
     }
@@ -175,7 +188,7 @@ k_vp_push(double* __restrict__ x, double* __restrict__ v, const double* __restri
     extern __shared__ double smem[];
     const int n = P.map.n;
     double* dsh = smem;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) dsh[i] = dcoef[i];
+    load_dcoef_ext(dsh, dcoef, n, K - 2 > 0 ? K - 2 : 0);
     __syncthreads();
     constexpr int U = 2;
     const long npairs = P.n >> 1;
@@ -270,7 +283,7 @@ k_gather(const double* __restrict__ x, long np, const double* __restrict__ coef 
 {
     extern __shared__ double smem[];
     const int n = map.n;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) smem[i] = coef[i];
+    for (int i = threadIdx.x; i < n + K; i += blockDim.x) smem[i] = coef[i < n ? i : i - n];   // periodic extension
     __syncthreads();
     const long stride = (long)gridDim.x * blockDim.x;
     for (long p = (long)blockIdx.x * blockDim.x + threadIdx.x; p < np; p += stride) {
@@ -279,13 +292,13 @@ k_gather(const double* __restrict__ x, long np, const double* __restrict__ coef 
         cell_of(map, x[p], b0, xi);
         double s;
         if (deriv) {
-            s = gather_dphi<K>(smem, n, b0, xi);
+            s = gather_dphi<K>(smem, b0, xi);
         } else {
             double N[K];
             bspline_uniform<K>(xi, N);
             s = 0.0;
 #pragma unroll
-            for (int j = 0; j < K; ++j) s = fma(N[j], smem[wrap_add(b0, j, n)], s);
+            for (int j = 0; j < K; ++j) s = fma(N[j], smem[b0 + j], s);
         }
         e[p] = scale * s;
     }
@@ -347,7 +360,7 @@ void launch_push_inst(vm_ctx* ctx, vm_field* f, vm_particles* p, double* out, co
     int grid, threads;
     vm_launch_geometry(ctx, &grid, &threads);
     if (threads > 512) threads = 512;
-    k_vp_push<K><<<grid, threads, (size_t)f->n * sizeof(double), ctx->stream>>>(p->x, p->v, p->w, f->dcoef, out, P);
+    k_vp_push<K><<<grid, threads, (size_t)(f->n + K) * sizeof(double), ctx->stream>>>(p->x, p->v, p->w, f->dcoef, out, P);
     VM_LAUNCHED(ctx);
 }
 
@@ -371,7 +384,7 @@ void launch_gather_inst(vm_ctx* ctx, vm_field* f, const double* x, long np, doub
     if (threads > 512) threads = 512;
     long need = (np + threads - 1) / threads;
     if (need < grid) grid = (int)(need > 0 ? need : 1);
-    k_gather<K><<<grid, threads, (size_t)f->n * sizeof(double), ctx->stream>>>(x, np, deriv ? f->dcoef : f->phi, e,
+    k_gather<K><<<grid, threads, (size_t)(f->n + K) * sizeof(double), ctx->stream>>>(x, np, deriv ? f->dcoef : f->phi, e,
                                                                              f->map, scale, deriv);
     VM_LAUNCHED(ctx);
 }
@@ -408,7 +421,7 @@ static void pass_with_deposit(vm_field* f, vm_particles* p, int pass_mode, int d
     vm_ctx* ctx = f->ctx;
     const int n = f->n;
     const int ncols = n;   // partial rows hold the grid only (the K/M sums live in their own rows)
-    DepositPlan pl = plan_deposit(ctx, n, pass_mode == MODE_PUSH_DEPOSIT, deposit_mode);
+    DepositPlan pl = plan_deposit(ctx, n, f->order - 1, pass_mode == MODE_PUSH_DEPOSIT ? n + f->order : 0, deposit_mode);
     P.map = f->map;
     P.n = p->n;
     P.rep_log2 = pl.rep_log2;
@@ -421,7 +434,7 @@ static void pass_with_deposit(vm_field* f, vm_particles* p, int pass_mode, int d
         out = f->rhs;
     } else {
         out = vm_partials(ctx, (size_t)pl.grid * ncols);
-        const size_t gdoubles = ((size_t)n << pl.rep_log2) * (size_t)(pl.threads / 32);
+        const size_t gdoubles = ((size_t)(n + f->order - 1) << pl.rep_log2) * (size_t)(pl.var == VAR_ATOMIC ? 1 : pl.threads / 32);
         if (n <= VM_FUSE_MAX_N && !ctx->no_fuse && gdoubles >= (size_t)2 * n + 1) {
             F.mode = (want_solve && ctx->nranks == 1) ? FINISH_REDUCE_SOLVE : FINISH_REDUCE;
             F.ticket = ctx->ticket;

@@ -61,7 +61,11 @@ __device__ __forceinline__ void vdeposit_one(double vp, double wp, bool active, 
     }
 #pragma unroll
     for (int j = 0; j < K; ++j) val[j] *= wp;
-    scatter<K, VAR>(wg, npar, rep_log2, rep, lane, c, val, active);
+    if (!active) {
+#pragma unroll
+        for (int j = 0; j < K; ++j) val[j] = 0.0;
+    }
+    scatter<K, VAR>(wg, rep_log2, rep, lane, c, val, active);
 }
 
 template <int K, int VAR>
@@ -113,7 +117,7 @@ k_v_deposit(const double* __restrict__ v, const double* __restrict__ w, long np,
         vdeposit_one<K, VAR>(active ? v[np - 1] : 0.0, active ? w[np - 1] : 0.0, active, m, cellpoly, wg, npar,
                              rep_log2, rep, lane);
     }
-    flush_grid<VAR>(grid, scratch, out, npar, rep_log2, nwarps, npar);
+    flush_grid<VAR>(grid, scratch, out, npar, 0, rep_log2, nwarps, npar);
     if (VAR != VAR_ATOMIC && F.mode != FINISH_NONE) finish_last_cta(F, out, gridDim.x, npar, grid, scratch);
 }
 
@@ -377,7 +381,7 @@ void launch_vdep_var(vm_vspline* s, const DepositPlan& pl, const double* v, cons
 void project_dev(vm_vspline* s, const double* v, const double* w, long np)
 {
     vm_ctx* ctx = s->ctx;
-    DepositPlan pl = plan_deposit(ctx, s->npar, false, VM_DEPOSIT_DETERMINISTIC);
+    DepositPlan pl = plan_deposit(ctx, s->npar, 0, 0, VM_DEPOSIT_DETERMINISTIC);
     double* out = vm_partials(ctx, (size_t)pl.grid * s->npar);
     FinishParams F{};
     const size_t gdoubles = ((size_t)s->npar << pl.rep_log2) * (size_t)(pl.threads / 32);
