@@ -196,7 +196,7 @@ def run_gpu(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         dist.init_process_group(backend="gloo")      # host-side rendezvous/barrier only
-    ctx = vm.init_distributed_context(local)
+    ctx = vm.init_distributed_context(local, peer_exchange=not args.no_peer)
     if args.no_fuse:
         ctx.set_tuning("no_fuse", 1)
     ntot = args.particles
@@ -298,6 +298,9 @@ def run_gpu(args):
     if rank == 0:
         cfg = workload_config(world)
         cfg["particles_total"] = ntot
+        cfg["collective"] = ("none" if world == 1 else
+                             "nccl_allreduce" if (args.no_peer or args.no_fuse or world > 8) else
+                             "fused_nvlink_peer_exchange_in_deposit_kernel")
         emit(({
             "metric": "particle-steps/sec", "value": value, "unit": "particle-steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -329,6 +332,7 @@ def main():
     ap.add_argument("--particles", type=int, default=N_TOTAL)
     ap.add_argument("--atomic", action="store_true", help="use the shared-atomic deposit variant (A/B)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-peer", action="store_true", help="NCCL all-reduce instead of the fused NVLink peer-memory exchange (A/B)")
     ap.add_argument("--no-fuse", action="store_true", help="separate reduce/solve kernels instead of the last-CTA finish (A/B)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

@@ -72,6 +72,14 @@ int vm_ctx_set_tuning(vm_ctx* ctx, const char* key, int value);
 int vm_comm_unique_id(void* out128);
 int vm_ctx_comm_init(vm_ctx* ctx, int rank, int nranks, const void* id128);
 int vm_ctx_comm_info(vm_ctx* ctx, int* rank, int* nranks);
+/* Optional: fused deposit + exchange + solve over NVLink peer memory (<= 8 ranks on one node).
+ * Every rank exports a 64-byte CUDA IPC handle of its inbox (vm_ctx_peer_handle), the handles are
+ * all-gathered over the host channel and passed in rank order to vm_ctx_peer_connect.  From then on
+ * the last CTA of the deposit pass writes this rank's partial grid into every peer's inbox, waits
+ * for the peers' grids, sums them in rank order (bit-identical on all ranks) and solves -- one
+ * kernel per step, no NCCL call on the hot path.  Without it the all-reduce uses NCCL. */
+int vm_ctx_peer_handle(vm_ctx* ctx, void* out64);
+int vm_ctx_peer_connect(vm_ctx* ctx, const void* handles_nranks_x_64);
 
 /* Device timing on the context's own stream (CUDA events), slots 0..15. */
 int vm_event_record(vm_ctx* ctx, int slot);

@@ -62,14 +62,18 @@ def _ngpus():
 
 
 @pytest.mark.timeout(600)
+@pytest.mark.parametrize("collective", ["peer", "nccl"])
 @pytest.mark.parametrize("world", [2, 4, 8])
-def test_sharded_run_matches_oracle(tmp_path, world):
+def test_sharded_run_matches_oracle(tmp_path, world, collective):
+    """collective = "peer": fused deposit + NVLink peer-memory exchange + solve (one kernel per step);
+    "nccl": ncclAllReduce between the deposit and the replicated solve."""
     if _ngpus() < world:
         pytest.skip(f"needs {world} GPUs")
     script = tmp_path / "worker.py"
     script.write_text(_WORKER.format(root=str(ROOT)))
+    env = dict(os.environ, VLASOV_B200_NO_PEER="1" if collective == "nccl" else "0")
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
                         "--master-addr", "127.0.0.1", "--master-port", str(29540 + world), str(script)],
-                       capture_output=True, text=True, timeout=580)
+                       capture_output=True, text=True, timeout=580, env=env)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert r.stdout.count("ok") == world

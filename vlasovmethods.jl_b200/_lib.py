@@ -9,8 +9,11 @@ import ctypes as C
 import subprocess
 from pathlib import Path
 
+import os
+
 _HERE = Path(__file__).resolve().parent
-LIB_PATH = _HERE / "libvlasov_b200.so"
+# VLASOV_B200_LIB selects another build of the same ABI (A/B experiments between kernel revisions)
+LIB_PATH = Path(os.environ.get("VLASOV_B200_LIB", _HERE / "libvlasov_b200.so"))
 
 _dp = C.POINTER(C.c_double)
 _vp = C.c_void_p
@@ -30,6 +33,8 @@ SIGNATURES = {
     "vm_comm_unique_id": (_i, [_vp]),
     "vm_ctx_comm_init": (_i, [_vp, _i, _i, _vp]),
     "vm_ctx_comm_info": (_i, [_vp, C.POINTER(_i), C.POINTER(_i)]),
+    "vm_ctx_peer_handle": (_i, [_vp, _vp]),
+    "vm_ctx_peer_connect": (_i, [_vp, _vp]),
     "vm_event_record": (_i, [_vp, _i]),
     "vm_event_elapsed_ms": (_i, [_vp, _i, _i, C.POINTER(_d)]),
     "vm_launch_count": (C.c_ulonglong, [_vp]),

@@ -62,6 +62,16 @@ class Context:
         buf = C.create_string_buffer(uid, 128) if uid is not None else None
         L.check(L.lib().vm_ctx_comm_init(self._h, int(rank), int(nranks), buf), self._h)
 
+    def peer_handle(self) -> bytes:
+        buf = C.create_string_buffer(64)
+        L.check(L.lib().vm_ctx_peer_handle(self._h, buf), self._h)
+        return buf.raw
+
+    def peer_connect(self, handles: bytes):
+        """handles: nranks x 64 bytes in rank order (all-gathered peer_handle() results)."""
+        buf = C.create_string_buffer(handles, len(handles))
+        L.check(L.lib().vm_ctx_peer_connect(self._h, buf), self._h)
+
     def comm_info(self):
         r, n = C.c_int(), C.c_int()
         L.check(L.lib().vm_ctx_comm_info(self._h, C.byref(r), C.byref(n)), self._h)

@@ -53,6 +53,14 @@ void vm_launch_geometry(vm_ctx* ctx, int* grid, int* threads)
     *grid = ctx->sm_count * c;
 }
 
+void vm_check_peer_error(vm_ctx* ctx)
+{
+    if (!ctx->peers_connected) return;
+    unsigned e = 0;
+    VM_CUDA(cudaMemcpy(&e, ctx->xerr, sizeof(e), cudaMemcpyDeviceToHost));
+    if (e) throw vm_error(VM_ERR_NCCL, "peer-memory exchange timed out waiting for another rank (ranks out of step?)");
+}
+
 void vm_prof_mark(vm_ctx* ctx)
 {
     if (!ctx->profile) return;
@@ -171,6 +179,11 @@ int vm_ctx_destroy(vm_ctx* ctx)
     if (!ctx) return VM_OK;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    if (ctx->peers_connected)
+        for (int r = 0; r < ctx->nranks; ++r)
+            if (r != ctx->rank && ctx->peer_inbox[r]) cudaIpcCloseMemHandle(ctx->peer_inbox[r]);
+    if (ctx->inbox) cudaFree(ctx->inbox);
+    if (ctx->xerr) cudaFree(ctx->xerr);
     if (ctx->nccl_comm) {
         try { nccl_api().CommDestroy(ctx->nccl_comm); } catch (...) {}
     }
@@ -189,6 +202,7 @@ int vm_sync(vm_ctx* ctx)
     VM_API_BEGIN(ctx)
     VM_REQUIRE(ctx != nullptr, "vm_sync: ctx is NULL");
     VM_CUDA(cudaStreamSynchronize(ctx->stream));
+    vm_check_peer_error(ctx);
     VM_API_END
 }
 
@@ -254,6 +268,43 @@ int vm_ctx_comm_init(vm_ctx* ctx, int rank, int nranks, const void* id128)
     }
     ctx->rank = rank;
     ctx->nranks = nranks;
+    VM_API_END
+}
+
+int vm_ctx_peer_handle(vm_ctx* ctx, void* out64)
+{
+    VM_API_BEGIN(ctx)
+    VM_REQUIRE(ctx != nullptr && out64 != nullptr, "vm_ctx_peer_handle: NULL argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle is 64 bytes");
+    if (!ctx->inbox) {
+        const size_t bytes = (size_t)VM_XFLAG_OFF * sizeof(double) + 2 * VM_MAX_PEERS * sizeof(unsigned long long);
+        VM_CUDA(cudaMalloc(&ctx->inbox, bytes));
+        VM_CUDA(cudaMemset(ctx->inbox, 0, bytes));
+        VM_CUDA(cudaMalloc(&ctx->xerr, sizeof(unsigned)));
+        VM_CUDA(cudaMemset(ctx->xerr, 0, sizeof(unsigned)));
+    }
+    cudaIpcMemHandle_t h;
+    VM_CUDA(cudaIpcGetMemHandle(&h, ctx->inbox));
+    std::memcpy(out64, &h, 64);
+    VM_API_END
+}
+
+int vm_ctx_peer_connect(vm_ctx* ctx, const void* handles)
+{
+    VM_API_BEGIN(ctx)
+    VM_REQUIRE(ctx != nullptr && handles != nullptr, "vm_ctx_peer_connect: NULL argument");
+    VM_REQUIRE(ctx->inbox != nullptr, "vm_ctx_peer_connect: call vm_ctx_peer_handle first");
+    VM_REQUIRE(ctx->nranks > 1 && ctx->nranks <= VM_MAX_PEERS, "vm_ctx_peer_connect: needs 2..8 ranks (vm_ctx_comm_init first)");
+    VM_REQUIRE(!ctx->peers_connected, "vm_ctx_peer_connect: already connected");
+    for (int r = 0; r < ctx->nranks; ++r) {
+        if (r == ctx->rank) { ctx->peer_inbox[r] = ctx->inbox; continue; }
+        cudaIpcMemHandle_t h;
+        std::memcpy(&h, (const char*)handles + 64 * r, 64);
+        void* ptr = nullptr;
+        VM_CUDA(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+        ctx->peer_inbox[r] = (double*)ptr;
+    }
+    ctx->peers_connected = true;
     VM_API_END
 }
 
@@ -425,6 +476,7 @@ int vm_particles_download_soa(vm_particles* p, double* x, double* v, double* w)
         if (w) copy_d2h(p->ctx, w, p->w, (size_t)p->n);
     }
     VM_CUDA(cudaStreamSynchronize(p->ctx->stream));
+    vm_check_peer_error(p->ctx);
     VM_API_END
 }
 

@@ -112,7 +112,24 @@ __device__ __forceinline__ void flush_grid(const double* __restrict__ grid, doub
 // GPU, also solves the periodic Poisson system -- the reduce and solve launches of a step disappear.
 // Used for n <= VM_FUSE_MAX_N; larger grids use the separate multi-CTA kernels.
 #define VM_FUSE_MAX_N 128
-enum { FINISH_NONE = 0, FINISH_REDUCE = 1, FINISH_REDUCE_SOLVE = 2 };
+enum { FINISH_NONE = 0, FINISH_REDUCE = 1, FINISH_REDUCE_SOLVE = 2, FINISH_EXCHANGE_SOLVE = 3 };
+
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ double ld_volatile_f64(const double* p)
+{
+    double v;
+    asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
 
 struct FinishParams {
     int mode;
@@ -122,6 +139,12 @@ struct FinishParams {
     double* phi;            // n
     double* dcoef;          // n
     double inv_h;
+    // FINISH_EXCHANGE_SOLVE: all-gather of the partial grids through NVLink peer memory
+    int nranks, rank;
+    unsigned long long seq;             // exchange number; slot set = seq & 1
+    double* inbox;                      // this rank's inbox
+    double* peer[VM_MAX_PEERS];         // every rank's inbox as mapped on this device (peer[rank] == inbox)
+    unsigned* err;
 };
 
 __device__ __forceinline__ void finish_last_cta(const FinishParams& F, const double* rows, int nrows, int n,
@@ -153,7 +176,36 @@ __device__ __forceinline__ void finish_last_cta(const FinishParams& F, const dou
         F.rhs[t] = s;
         r_sh[t] = s;
     }
-    if (F.mode == FINISH_REDUCE_SOLVE) {
+    if (F.mode == FINISH_EXCHANGE_SOLVE) {
+        // Fused collective: every rank writes its partial grid into slot [set][rank] of EVERY rank's
+        // inbox (P2P stores over NVLink), publishes a release flag, waits for all peers' flags and sums
+        // the slots in rank order -- the same bits on every rank.  Two slot sets: a peer can be at most
+        // one exchange ahead (it needs this rank's flag for the next one).
+        __syncthreads();
+        const int set = (int)(F.seq & 1ull);
+        for (int idx = t; idx < n * F.nranks; idx += T) {
+            const int r = idx / n, i = idx - r * n;
+            F.peer[r][(size_t)(set * VM_MAX_PEERS + F.rank) * VM_XSLOT + i] = r_sh[i];
+        }
+        __threadfence_system();
+        __syncthreads();
+        if (t < F.nranks) {
+            st_release_sys_u64((unsigned long long*)(F.peer[t] + VM_XFLAG_OFF) + set * VM_MAX_PEERS + F.rank, F.seq);
+            const unsigned long long* flag = (const unsigned long long*)(F.inbox + VM_XFLAG_OFF) + set * VM_MAX_PEERS + t;
+            const long long t0 = clock64();
+            while (ld_acquire_sys_u64(flag) < F.seq) {
+                if (clock64() - t0 > (1ll << 34)) { atomicExch(F.err, 1u); break; }   // ~8 s: give up, host reports
+            }
+        }
+        __syncthreads();
+        if (t < n) {
+            double s = 0.0;
+            for (int r = 0; r < F.nranks; ++r) s += ld_volatile_f64(F.inbox + (size_t)(set * VM_MAX_PEERS + r) * VM_XSLOT + t);
+            F.rhs[t] = s;
+            r_sh[t] = s;
+        }
+    }
+    if (F.mode == FINISH_REDUCE_SOLVE || F.mode == FINISH_EXCHANGE_SOLVE) {
         __syncthreads();
         if (t < 32) {                // mean in a fixed order: strided lane sums, then the xor tree
             double s = 0.0;

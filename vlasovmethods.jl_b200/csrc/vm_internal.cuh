@@ -17,6 +17,9 @@
 #define VM_FULL_MASK 0xffffffffu
 #define VM_DIAG_COLS 4          // extra columns appended to a partial row: [sum w v^2, sum w v, sum w, spare]
 #define VM_MAX_EVENTS 16
+#define VM_MAX_PEERS 8          // ranks of the fused peer-memory exchange (one NVSwitch node)
+#define VM_XSLOT 136            // doubles per (set, rank) inbox slot (>= VM_FUSE_MAX_N)
+#define VM_XFLAG_OFF (2 * VM_MAX_PEERS * VM_XSLOT)   // flags (u64) follow the slots
 
 struct vm_error : public std::runtime_error {
     int code;
@@ -52,6 +55,12 @@ struct vm_ctx {
     void* nccl_comm = nullptr;
     int rank = 0, nranks = 1;
     unsigned* ticket = nullptr;          // device counter for the last-CTA finish (always zero between launches)
+    // fused peer-memory exchange (vm_ctx_peer_connect): inbox = [2 sets][VM_MAX_PEERS][VM_XSLOT] doubles + flags
+    double* inbox = nullptr;
+    double* peer_inbox[VM_MAX_PEERS] = {};
+    bool peers_connected = false;
+    unsigned long long xseq = 0;         // exchange sequence number (identical on all ranks)
+    unsigned* xerr = nullptr;            // device: set when a peer wait timed out
     // scratch: per-CTA partial rows for the fixed-order reductions
     double* partials = nullptr;
     size_t partials_elems = 0;
@@ -111,7 +120,8 @@ double* vm_partials(vm_ctx* ctx, size_t elems);   // grow-only device scratch
 double* vm_pinned(vm_ctx* ctx, size_t elems);     // grow-only pinned host scratch
 void vm_allreduce_sum(vm_ctx* ctx, double* dev, size_t count);  // no-op when nranks == 1
 void vm_launch_geometry(vm_ctx* ctx, int* grid, int* threads);
-void vm_prof_mark(vm_ctx* ctx);   // records the next event of a start/stop pair when profiling is on
+void vm_prof_mark(vm_ctx* ctx);
+void vm_check_peer_error(vm_ctx* ctx);   // after a stream sync: throws if a peer exchange timed out   // records the next event of a start/stop pair when profiling is on
 
 #define VM_API_BEGIN(ctxexpr)          \
     vm_ctx* ctx__ = (ctxexpr);         \
@@ -166,22 +176,35 @@ __device__ __forceinline__ void bspline_uniform(double xi, double (&N)[K])
 }
 
 // (x - a)/h -> (cell index mod n incl. the index rotation, fractional coordinate in [0,1)).
-// floor() without the slow fp64<->int conversion pipe: adding 1.5*2^52 leaves round-to-nearest(t) in
-// the low mantissa word; one compare turns the rounding into a floor.  Valid for |t| < 2^30.
+// Two floor() flavours, chosen per kernel from A/B measurements on B200 (profiles/):
+//  CONV = true : FRND.F64.FLOOR + F2I.F64 -- 2 instructions, but on the quarter-rate conversion pipe;
+//                best where issue slots are scarce and there is one cell lookup per particle (deposit).
+//  CONV = false: adding 1.5*2^52 leaves round-to-nearest(t) in the low mantissa word and one compare
+//                turns the rounding into a floor -- 5 full-rate fp64 instructions; best for the fused
+//                push+deposit pass (two lookups per particle saturate the conversion pipe).
+// Valid for |t| < 2^30; the result is clamped in-bounds for garbage positions.
+template <bool CONV>
 __device__ __forceinline__ void cell_of(const CellMap& m, double x, int& base, double& xi)
 {
     const double t = fma(x, m.inv_h, m.off);
-    const double big = 6755399441055744.0;             // 1.5 * 2^52
-    const double tm = t + big;
-    double r = tm - big;                                // round-to-nearest-even(t), exact
-    int c = __double2loint(tm);
-    if (r > t) { r -= 1.0; c -= 1; }
-    xi = t - r;
-    const unsigned u = (unsigned)(c + m.bias);          // in [0, 2^31)
+    int c;
+    if (CONV) {
+        const double r = floor(t);
+        c = __double2int_rd(t);
+        xi = t - r;
+    } else {
+        const double big = 6755399441055744.0;             // 1.5 * 2^52
+        const double tm = t + big;
+        double r = tm - big;                                // round-to-nearest-even(t), exact
+        c = __double2loint(tm);
+        if (r > t) { r -= 1.0; c -= 1; }
+        xi = t - r;
+    }
+    const unsigned u = (unsigned)(c + m.bias);              // in [0, 2^31)
     const unsigned q = __umulhi(u, m.inv_n);
     unsigned rr = u - q * (unsigned)m.n;
     if (rr >= (unsigned)m.n) rr -= (unsigned)m.n;
-    base = (int)min(rr, (unsigned)m.n - 1u);             // in-bounds even for garbage positions (|t| >= 2^30)
+    base = (int)min(rr, (unsigned)m.n - 1u);                // in-bounds even for garbage positions (|t| >= 2^30)
 }
 
 __device__ __forceinline__ int wrap_add(int i, int j, int n)

@@ -169,6 +169,10 @@ __device__ __forceinline__ void eval_f_df(const double* __restrict__ psh, const 
     df = (K > 1) ? sd * m.inv_h : 0.0;
 }
 
+// Streaming helper: each thread handles U pairs (4 particles for U = 2) per iteration, all loads issued
+// before any use, so that enough bytes are in flight for these low-byte passes.
+#define VM_STREAM_PAIRS 2
+
 // five unweighted particle sums: [sum f, sum v f, sum v^2 f, sum f', sum v f']
 template <int K>
 __global__ void __launch_bounds__(512, 2)
@@ -178,9 +182,7 @@ k_v_moments(const double* __restrict__ v, long np, VCell m, const double* __rest
     for (int i = threadIdx.x; i < m.ncell * K; i += blockDim.x) psh[i] = poly[i];
     __syncthreads();
     double s[5] = {0., 0., 0., 0., 0.};
-    const long stride = (long)gridDim.x * blockDim.x;
-    for (long p = (long)blockIdx.x * blockDim.x + threadIdx.x; p < np; p += stride) {
-        const double vp = ld_stream(v + p);
+    auto acc = [&](double vp) {
         double f, df;
         eval_f_df<K>(psh, m, vp, f, df);
         s[0] += f;
@@ -188,7 +190,21 @@ k_v_moments(const double* __restrict__ v, long np, VCell m, const double* __rest
         s[2] = fma(vp * vp, f, s[2]);
         s[3] += df;
         s[4] = fma(vp, df, s[4]);
+    };
+    constexpr int U = VM_STREAM_PAIRS;
+    const long npairs = np >> 1;
+    const long stride = (long)gridDim.x * blockDim.x;
+    const long gtid = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (long base = gtid; base < npairs; base += U * stride) {
+        double2 c[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (base + u * stride < npairs) c[u] = ld_stream2(v + 2 * (base + u * stride));
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (base + u * stride < npairs) { acc(c[u].x); acc(c[u].y); }
     }
+    if ((np & 1) && gtid == 0) acc(v[np - 1]);
     __shared__ double red[5][32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
 #pragma unroll
@@ -232,13 +248,26 @@ k_v_rhs(const double* __restrict__ v, long np, VCell m, const double* __restrict
     for (int i = threadIdx.x; i < m.ncell * K; i += blockDim.x) psh[i] = poly[i];
     __syncthreads();
     const double A1 = mom[5], A2 = mom[6];
-    const long stride = (long)gridDim.x * blockDim.x;
-    for (long p = (long)blockIdx.x * blockDim.x + threadIdx.x; p < np; p += stride) {
-        const double vp = ld_stream(v + p);
+    auto rhs = [&](double vp) {
         double f, df;
         eval_f_df<K>(psh, m, vp, f, df);
-        st_stream(vdot + p, -nu * (df + fma(A2, vp, A1) * f));
+        return -nu * (df + fma(A2, vp, A1) * f);
+    };
+    constexpr int U = VM_STREAM_PAIRS;
+    const long npairs = np >> 1;
+    const long stride = (long)gridDim.x * blockDim.x;
+    const long gtid = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (long base = gtid; base < npairs; base += U * stride) {
+        double2 c[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (base + u * stride < npairs) c[u] = ld_stream2(v + 2 * (base + u * stride));
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (base + u * stride < npairs)
+                st_stream2(vdot + 2 * (base + u * stride), make_double2(rhs(c[u].x), rhs(c[u].y)));
     }
+    if ((np & 1) && gtid == 0) vdot[np - 1] = rhs(v[np - 1]);
 }
 
 // f_s and f_s' at arbitrary points (plotting / tests)
@@ -264,13 +293,25 @@ k_rk_combine(const double* v, const double* __restrict__ k1, const double* __res
              const double* __restrict__ k3, const double* __restrict__ k4, double a1, double a2, double a3, double a4,
              double dt, long np, double* q /* may alias v (final update) */)
 {
+    const long npairs = np >> 1;
     const long stride = (long)gridDim.x * blockDim.x;
-    for (long p = (long)blockIdx.x * blockDim.x + threadIdx.x; p < np; p += stride) {
-        double s = a1 * ld_stream(k1 + p);
-        if (k2) s = fma(a2, ld_stream(k2 + p), s);
-        if (k3) s = fma(a3, ld_stream(k3 + p), s);
-        if (k4) s = fma(a4, ld_stream(k4 + p), s);
-        st_stream(q + p, fma(dt, s, v[p]));
+    const long gtid = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (long p = gtid; p < npairs; p += stride) {
+        const double2 vv = ld_stream2(v + 2 * p);
+        double2 s = ld_stream2(k1 + 2 * p);
+        s.x *= a1; s.y *= a1;
+        if (k2) { const double2 t = ld_stream2(k2 + 2 * p); s.x = fma(a2, t.x, s.x); s.y = fma(a2, t.y, s.y); }
+        if (k3) { const double2 t = ld_stream2(k3 + 2 * p); s.x = fma(a3, t.x, s.x); s.y = fma(a3, t.y, s.y); }
+        if (k4) { const double2 t = ld_stream2(k4 + 2 * p); s.x = fma(a4, t.x, s.x); s.y = fma(a4, t.y, s.y); }
+        st_stream2(q + 2 * p, make_double2(fma(dt, s.x, vv.x), fma(dt, s.y, vv.y)));
+    }
+    if ((np & 1) && gtid == 0) {
+        const long p = np - 1;
+        double s = a1 * k1[p];
+        if (k2) s = fma(a2, k2[p], s);
+        if (k3) s = fma(a3, k3[p], s);
+        if (k4) s = fma(a4, k4[p], s);
+        q[p] = fma(dt, s, v[p]);
     }
 }
 

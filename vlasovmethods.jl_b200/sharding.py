@@ -20,7 +20,7 @@ def shard_bounds(n_total: int, rank: int, world: int) -> Tuple[int, int]:
     return first, first + base + (1 if rank < extra else 0)
 
 
-def init_distributed_context(device: int | None = None) -> Context:
+def init_distributed_context(device: int | None = None, peer_exchange: bool = True) -> Context:
     """Create the Context for this torchrun rank and wire its NCCL communicator.
 
     The 128-byte NCCL unique id is broadcast from rank 0 over torch.distributed (any host channel
@@ -38,4 +38,10 @@ def init_distributed_context(device: int | None = None) -> Context:
         t = torch.tensor(list(uid), dtype=torch.uint8)
         dist.broadcast(t, src=0)
         ctx.comm_init(rank, world, bytes(t.tolist()))
+        if peer_exchange and world <= 8 and os.environ.get("VLASOV_B200_NO_PEER", "0") != "1":
+            # fused deposit + exchange + solve over NVLink peer memory: all-gather the CUDA IPC handles
+            mine = torch.tensor(list(ctx.peer_handle()), dtype=torch.uint8)
+            allh = [torch.zeros(64, dtype=torch.uint8) for _ in range(world)]
+            dist.all_gather(allh, mine)
+            ctx.peer_connect(b"".join(bytes(h.tolist()) for h in allh))
     return ctx
