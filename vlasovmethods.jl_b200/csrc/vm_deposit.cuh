@@ -164,7 +164,16 @@ __device__ __forceinline__ void finish_last_cta(const FinishParams& F, const dou
     if (t < n * P) {
         const int i = t % n, part = t / n;
         double s = 0.0;
-        for (int r = part; r < nrows; r += P) s += __ldcg(rows + (size_t)r * n + i);
+        for (int r = part; r < nrows; r += 8 * P) {      // 8 independent L2 loads in flight, summed in row order
+            double vals[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int rr = r + u * P;
+                vals[u] = (rr < nrows) ? __ldcg(rows + (size_t)rr * n + i) : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) s += vals[u];
+        }
         scratch[part * n + i] = s;
     }
     __syncthreads();

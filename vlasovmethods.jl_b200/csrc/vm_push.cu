@@ -102,6 +102,9 @@ k_vp_pass(double* __restrict__ x, double* __restrict__ v, const double* __restri
     const int gtotal = (VAR == VAR_ATOMIC) ? gsz : gsz * nwarps;
     double* scratch = grid + gtotal;
     for (int i = threadIdx.x; i < gtotal; i += blockDim.x) grid[i] = 0.0;
+    // Programmatic dependent launch: everything above overlaps the previous kernel's tail (its last
+    // CTA is still reducing / exchanging / solving); nothing it wrote is read before this point.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     if (MODE == MODE_PUSH_DEPOSIT) load_dcoef_ext(dsh, dcoef, n, K - 2 > 0 ? K - 2 : 0);
     __syncthreads();
     double* wg = (VAR == VAR_ATOMIC) ? grid : grid + warp * gsz;
@@ -159,6 +162,8 @@ k_vp_pass(double* __restrict__ x, double* __restrict__ v, const double* __restri
             for (int u = 0; u < U; ++u) A[u] = B[u];
         }
     }
+    // let the next kernel of the stream start its prologue while this grid drains and finishes
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if ((P.n & 1) && blockIdx.x == 0 && warp == 0) {   // odd particle count: last particle, lane 0 of one warp
         const bool active = (lane == 0);
         double xp = 0., vp = 0., wp = 0.;
@@ -338,8 +343,18 @@ void launch_pass_inst(vm_ctx* ctx, const DepositPlan& pl, double* x, double* v, 
         VM_CUDA(cudaFuncSetAttribute(k_vp_pass<K, VAR, MODE, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
         conf = pl.smem;
     }
-    k_vp_pass<K, VAR, MODE, U><<<pl.grid, pl.threads, pl.smem, ctx->stream>>>(x, v, w, dcoef, out, P, F);
-    VM_LAUNCHED(ctx);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(pl.grid);
+    cfg.blockDim = dim3(pl.threads);
+    cfg.dynamicSmemBytes = pl.smem;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // PDL: see griddepcontrol.wait in the kernel
+    attr[0].val.programmaticStreamSerializationAllowed = ctx->no_pdl ? 0 : 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    VM_CUDA(cudaLaunchKernelEx(&cfg, k_vp_pass<K, VAR, MODE, U>, x, v, w, dcoef, out, P, F));
+    ++ctx->launches;
 }
 
 template <int K, int MODE>
