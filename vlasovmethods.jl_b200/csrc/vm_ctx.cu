@@ -419,6 +419,7 @@ int vm_particles_create(vm_ctx* ctx, long n, vm_particles** out)
     VM_API_BEGIN(ctx)
     VM_REQUIRE(ctx != nullptr && out != nullptr, "vm_particles_create: NULL argument");
     VM_REQUIRE(n >= 0, "vm_particles_create: negative size");
+    VM_REQUIRE(n < (1L << 33) - (1L << 24), "vm_particles_create: at most 2^33 - 2^24 particles per GPU (32-bit pair indices)");
     *out = nullptr;
     vm_particles* p = new vm_particles();
     p->ctx = ctx;

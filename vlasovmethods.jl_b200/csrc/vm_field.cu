@@ -245,6 +245,8 @@ int vm_field_create(vm_ctx* ctx, double a, double b, int order, int n_basis, int
         int sh = ((index_shift % n) + n) % n;
         f->map.bias = n * ((1 << 30) / n) + sh;
         f->map.inv_n = (unsigned)(0x100000000ull / (unsigned long long)n);
+        f->map.mask = ((n & (n - 1)) == 0) ? n - 1 : -1;
+        f->map.shift = sh;
 
         ld mass[vmhost::MAXK], stiff[vmhost::MAXK];
         vmhost::uniform_stencils(k, mass, stiff);

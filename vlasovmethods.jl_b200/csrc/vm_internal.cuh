@@ -84,6 +84,8 @@ struct CellMap {
     int n;            // number of cells == number of periodic basis functions
     int bias;         // multiple of n plus index shift; makes the raw cell index positive
     unsigned inv_n;   // floor(2^32 / n), for the fast modulo
+    int mask;         // n - 1 when n is a power of two (then (c + shift) & mask replaces the modulo), else -1
+    int shift;        // index rotation reduced to [0, n)
 };
 
 struct vm_field {
@@ -153,26 +155,53 @@ void vm_check_peer_error(vm_ctx* ctx);   // after a stream sync: throws if a pee
 // ------------------------------------------------------------------ device --
 #ifdef __CUDACC__
 
-// K nonzero uniform B-splines of order K at local coordinate xi in [0,1), increasing index.
-// de Boor recursion specialised to unit knot spacing (all denominators are the integers 1..K-1).
+// K nonzero uniform B-splines of order K at local coordinate xi in [0,1), increasing index, times a
+// common factor w (the particle weight; pass 1.0 for plain values).  Orders 2-4 use closed forms that
+// exploit the symmetry B_j(xi) = B_{K-1-j}(1 - xi) (14 fp64 instructions for the weighted cubic instead
+// of 25 for the recursion); orders 5 and 6 use the de Boor recursion specialised to unit knot spacing.
+template <int K>
+__device__ __forceinline__ void bspline_uniform_w(double xi, double w, double (&N)[K])
+{
+    if (K == 1) {
+        N[0] = w;
+    } else if (K == 2) {
+        N[1] = xi * w;
+        N[0] = w - N[1];
+    } else if (K == 3) {
+        const double om = 1.0 - xi, wh = 0.5 * w;
+        N[0] = (om * om) * wh;
+        N[2] = (xi * xi) * wh;
+        N[1] = fma(xi, om, 0.5) * w;
+    } else if (K == 4) {
+        const double om = 1.0 - xi, w6 = w * (1.0 / 6.0);
+        const double x2 = xi * xi, o2 = om * om;
+        N[0] = (o2 * om) * w6;
+        N[3] = (x2 * xi) * w6;
+        N[1] = fma(x2, fma(0.5, xi, -1.0), 2.0 / 3.0) * w;
+        N[2] = fma(o2, fma(0.5, om, -1.0), 2.0 / 3.0) * w;
+    } else {
+        N[0] = w;
+#pragma unroll
+        for (int j = 1; j < K; ++j) {
+            const double inv = 1.0 / (double)j;
+            double saved = 0.0;
+#pragma unroll
+            for (int r = 0; r < j; ++r) {
+                const double temp = N[r] * inv;
+                const double right = (double)(r + 1) - xi;
+                const double left = xi + (double)(j - r - 1);
+                N[r] = fma(right, temp, saved);
+                saved = left * temp;
+            }
+            N[j] = saved;
+        }
+    }
+}
+
 template <int K>
 __device__ __forceinline__ void bspline_uniform(double xi, double (&N)[K])
 {
-    N[0] = 1.0;
-#pragma unroll
-    for (int j = 1; j < K; ++j) {
-        const double inv = 1.0 / (double)j;
-        double saved = 0.0;
-#pragma unroll
-        for (int r = 0; r < j; ++r) {
-            const double temp = N[r] * inv;
-            const double right = (double)(r + 1) - xi;
-            const double left = xi + (double)(j - r - 1);
-            N[r] = fma(right, temp, saved);
-            saved = left * temp;
-        }
-        N[j] = saved;
-    }
+    bspline_uniform_w<K>(xi, 1.0, N);
 }
 
 // (x - a)/h -> (cell index mod n incl. the index rotation, fractional coordinate in [0,1)).
@@ -183,7 +212,7 @@ __device__ __forceinline__ void bspline_uniform(double xi, double (&N)[K])
 //                turns the rounding into a floor -- 5 full-rate fp64 instructions; best for the fused
 //                push+deposit pass (two lookups per particle saturate the conversion pipe).
 // Valid for |t| < 2^30; the result is clamped in-bounds for garbage positions.
-template <bool CONV>
+template <bool CONV, bool POW2 = false>
 __device__ __forceinline__ void cell_of(const CellMap& m, double x, int& base, double& xi)
 {
     const double t = fma(x, m.inv_h, m.off);
@@ -200,11 +229,15 @@ __device__ __forceinline__ void cell_of(const CellMap& m, double x, int& base, d
         if (r > t) { r -= 1.0; c -= 1; }
         xi = t - r;
     }
-    const unsigned u = (unsigned)(c + m.bias);              // in [0, 2^31)
-    const unsigned q = __umulhi(u, m.inv_n);
-    unsigned rr = u - q * (unsigned)m.n;
-    if (rr >= (unsigned)m.n) rr -= (unsigned)m.n;
-    base = (int)min(rr, (unsigned)m.n - 1u);                // in-bounds even for garbage positions (|t| >= 2^30)
+    if (POW2) {                                             // power-of-two grid: the modulo is a mask
+        base = (c + m.shift) & m.mask;
+    } else {
+        const unsigned u = (unsigned)(c + m.bias);          // in [0, 2^31)
+        const unsigned q = __umulhi(u, m.inv_n);
+        unsigned rr = u - q * (unsigned)m.n;
+        if (rr >= (unsigned)m.n) rr -= (unsigned)m.n;
+        base = (int)min(rr, (unsigned)m.n - 1u);            // in-bounds even for garbage positions (|t| >= 2^30)
+    }
 }
 
 __device__ __forceinline__ int wrap_add(int i, int j, int n)

@@ -53,7 +53,9 @@ __device__ __forceinline__ void load_dcoef_ext(double* __restrict__ dsh, const d
 }
 
 // --------------------------------------------------------- the fused pass ---
-template <int K, int VAR, int MODE>
+// SPLIT: two half kicks (new-API Strang) instead of one.  The fused mode always applies the two
+// separately rounded half drifts of consecutive Strang steps (drift1 then drift2).
+template <int K, int VAR, int MODE, bool SPLIT, bool POW2>
 __device__ __forceinline__ void process(double& xp, double& vp, double wp, bool active, const PassParams& P,
                                         const double* __restrict__ dsh, double* __restrict__ wg, int rep, int lane)
 {
@@ -61,21 +63,17 @@ __device__ __forceinline__ void process(double& xp, double& vp, double wp, bool 
     double xi;
     constexpr bool CONV = (MODE == MODE_DEPOSIT);      // see cell_of: measured per mode
     if (MODE == MODE_PUSH_DEPOSIT) {
-        cell_of<CONV>(P.map, xp, b0, xi);
+        cell_of<CONV, POW2>(P.map, xp, b0, xi);
         const double dphi = gather_dphi<K>(dsh, b0, xi);
         // literal (unfused) update order of s_acceleration!: v = v - dt * phi'
         vp = __dadd_rn(vp, __dmul_rn(P.kick, dphi));
-        if (P.kick2 != 0.0) vp = __dadd_rn(vp, __dmul_rn(P.kick2, dphi));
+        if (SPLIT) vp = __dadd_rn(vp, __dmul_rn(P.kick2, dphi));
     }
-    if (MODE != MODE_DEPOSIT) {
-        xp = __dadd_rn(xp, __dmul_rn(P.drift1, vp));
-        if (P.drift2 != 0.0) xp = __dadd_rn(xp, __dmul_rn(P.drift2, vp));
-    }
-    cell_of<CONV>(P.map, xp, b0, xi);
+    if (MODE != MODE_DEPOSIT) xp = __dadd_rn(xp, __dmul_rn(P.drift1, vp));
+    if (MODE == MODE_PUSH_DEPOSIT) xp = __dadd_rn(xp, __dmul_rn(P.drift2, vp));
+    cell_of<CONV, POW2>(P.map, xp, b0, xi);
     double val[K];
-    bspline_uniform<K>(xi, val);
-#pragma unroll
-    for (int j = 0; j < K; ++j) val[j] *= wp;      // inactive lanes carry wp == 0
+    bspline_uniform_w<K>(xi, wp, val);                 // inactive lanes carry wp == 0
     scatter<K, VAR>(wg, P.rep_log2, rep, lane, b0, val, active);
 }
 
@@ -84,10 +82,9 @@ struct PairBuf {
     double2 x, v, w;
 };
 
-// U = pairs of particles each thread keeps in flight per half-iteration.  The loop is unrolled twice
-// over two register buffer sets (A is processed while B is in flight and vice versa): no register
-// rotation, loads one half-iteration ahead.
-template <int K, int VAR, int MODE, int U>
+// U = pairs of particles each thread keeps in flight per (half-)iteration, loads one iteration ahead.
+// Pair indices are 32-bit (N < 2^32 particles per GPU).
+template <int K, int VAR, int MODE, int U, bool SPLIT, bool POW2>
 __global__ void __launch_bounds__(1024, 1)
 k_vp_pass(double* __restrict__ x, double* __restrict__ v, const double* __restrict__ w,
           const double* __restrict__ dcoef, double* __restrict__ out, const PassParams P, const FinishParams F)
@@ -110,54 +107,57 @@ k_vp_pass(double* __restrict__ x, double* __restrict__ v, const double* __restri
     double* wg = (VAR == VAR_ATOMIC) ? grid : grid + warp * gsz;
     const int rep = ((VAR == VAR_ATOMIC) ? warp : lane) & ((1 << P.rep_log2) - 1);
 
-    const long npairs = P.n >> 1;
-    const long stride = (long)gridDim.x * blockDim.x;
-    const long gtid = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long iters = (npairs + U * stride - 1) / (U * stride);   // uniform trip count: the scatter is warp-collective
+    const unsigned npairs = (unsigned)(P.n >> 1);
+    const unsigned stride = gridDim.x * blockDim.x;
+    const unsigned gtid = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned chunk = U * stride;
+    const unsigned iters = (npairs + chunk - 1) / chunk;   // uniform trip count: the scatter is warp-collective
 
     PairBuf<MODE> A[U], B[U];
-    auto load = [&](PairBuf<MODE> (&buf)[U], long it) {
+    auto load = [&](PairBuf<MODE> (&buf)[U], unsigned q0) {   // q0 = first pair of this thread's slice
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const long q = (it * U + u) * stride + gtid;
+            const unsigned q = q0 + u * stride;
             buf[u].w = make_double2(0., 0.);            // out-of-range pairs deposit nothing
             if (q < npairs) {
-                buf[u].x = ld_stream2(x + 2 * q);
-                if (MODE != MODE_DEPOSIT) buf[u].v = ld_stream2(v + 2 * q);
-                buf[u].w = ld_stream2(w + 2 * q);
+                buf[u].x = ld_stream2(x + 2 * (size_t)q);
+                if (MODE != MODE_DEPOSIT) buf[u].v = ld_stream2(v + 2 * (size_t)q);
+                buf[u].w = ld_stream2(w + 2 * (size_t)q);
             }
         }
     };
-    auto work = [&](PairBuf<MODE> (&buf)[U], long it) {
+    auto work = [&](PairBuf<MODE> (&buf)[U], unsigned q0) {
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const long q = (it * U + u) * stride + gtid;
+            const unsigned q = q0 + u * stride;
             const bool active = q < npairs;
-            process<K, VAR, MODE>(buf[u].x.x, buf[u].v.x, buf[u].w.x, active, P, dsh, wg, rep, lane);
-            process<K, VAR, MODE>(buf[u].x.y, buf[u].v.y, buf[u].w.y, active, P, dsh, wg, rep, lane);
+            process<K, VAR, MODE, SPLIT, POW2>(buf[u].x.x, buf[u].v.x, buf[u].w.x, active, P, dsh, wg, rep, lane);
+            process<K, VAR, MODE, SPLIT, POW2>(buf[u].x.y, buf[u].v.y, buf[u].w.y, active, P, dsh, wg, rep, lane);
             if (active && MODE != MODE_DEPOSIT) {
-                st_stream2(x + 2 * q, buf[u].x);
-                if (MODE == MODE_PUSH_DEPOSIT) st_stream2(v + 2 * q, buf[u].v);
+                st_stream2(x + 2 * (size_t)q, buf[u].x);
+                if (MODE == MODE_PUSH_DEPOSIT) st_stream2(v + 2 * (size_t)q, buf[u].v);
             }
         }
     };
 #pragma unroll
     for (int u = 0; u < U; ++u) A[u].x = A[u].v = B[u].x = B[u].v = make_double2(0., 0.);
-    load(A, 0);
+    // q advances by `chunk` per iteration; npairs + 3*chunk < 2^32 is guaranteed by vm_particles_create
+    unsigned q = gtid;
+    load(A, q);
     if (MODE == MODE_DEPOSIT) {
         // 16 B/particle pass, issue-bound: unrolled twice over the two buffer sets (no register moves)
-        for (long it = 0; it < iters; it += 2) {
-            load(B, it + 1);
-            work(A, it);
-            load(A, it + 2);
-            work(B, it + 1);    // all-inactive when iters is odd (costs one idle half-iteration)
+        for (unsigned it = 0; it < iters; it += 2, q += 2 * chunk) {
+            load(B, q + chunk);
+            work(A, q);
+            load(A, q + 2 * chunk);
+            work(B, q + chunk);    // all-inactive when iters is odd (costs one idle half-iteration)
         }
     } else {
         // 32-40 B/particle passes, HBM-bound: keeping the next pair's loads at the very top of the
         // iteration measured 5 % faster than the unrolled form (ptxas sinks the loads otherwise)
-        for (long it = 0; it < iters; ++it) {
-            load(B, it + 1);
-            work(A, it);
+        for (unsigned it = 0; it < iters; ++it, q += chunk) {
+            load(B, q + chunk);
+            work(A, q);
 #pragma unroll
             for (int u = 0; u < U; ++u) A[u] = B[u];
         }
@@ -172,7 +172,7 @@ k_vp_pass(double* __restrict__ x, double* __restrict__ v, const double* __restri
             if (MODE != MODE_DEPOSIT) vp = v[P.n - 1];
             wp = w[P.n - 1];
         }
-        process<K, VAR, MODE>(xp, vp, wp, active, P, dsh, wg, rep, lane);
+        process<K, VAR, MODE, SPLIT, POW2>(xp, vp, wp, active, P, dsh, wg, rep, lane);
         if (active && MODE != MODE_DEPOSIT) {
             x[P.n - 1] = xp;
             if (MODE == MODE_PUSH_DEPOSIT) v[P.n - 1] = vp;
@@ -332,7 +332,7 @@ __global__ void __launch_bounds__(512, 2) k_drift(double* __restrict__ x, const 
 // ================================================================ host ======
 namespace {
 
-template <int K, int VAR, int MODE>
+template <int K, int VAR, int MODE, bool SPLIT, bool POW2>
 void launch_pass_inst(vm_ctx* ctx, const DepositPlan& pl, double* x, double* v, const double* w,
                       const double* dcoef, double* out, const PassParams& P, const FinishParams& F)
 {
@@ -340,7 +340,7 @@ void launch_pass_inst(vm_ctx* ctx, const DepositPlan& pl, double* x, double* v, 
     static size_t configured[64] = {};   // per device: max dynamic smem already opted into for this instantiation
     size_t& conf = configured[ctx->device & 63];
     if (pl.smem > conf) {
-        VM_CUDA(cudaFuncSetAttribute(k_vp_pass<K, VAR, MODE, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+        VM_CUDA(cudaFuncSetAttribute(k_vp_pass<K, VAR, MODE, U, SPLIT, POW2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
         conf = pl.smem;
     }
     cudaLaunchConfig_t cfg{};
@@ -353,7 +353,7 @@ void launch_pass_inst(vm_ctx* ctx, const DepositPlan& pl, double* x, double* v, 
     attr[0].val.programmaticStreamSerializationAllowed = ctx->no_pdl ? 0 : 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    VM_CUDA(cudaLaunchKernelEx(&cfg, k_vp_pass<K, VAR, MODE, U>, x, v, w, dcoef, out, P, F));
+    VM_CUDA(cudaLaunchKernelEx(&cfg, k_vp_pass<K, VAR, MODE, U, SPLIT, POW2>, x, v, w, dcoef, out, P, F));
     ++ctx->launches;
 }
 
@@ -361,11 +361,20 @@ template <int K, int MODE>
 void launch_pass_var(vm_ctx* ctx, const DepositPlan& pl, double* x, double* v, const double* w,
                      const double* dcoef, double* out, const PassParams& P, const FinishParams& F)
 {
+    const bool split = (MODE == MODE_PUSH_DEPOSIT) && P.kick2 != 0.0;
+    // the mask form of the periodic wrap is only specialised for the lane-private variant (small grids)
+    const bool pow2 = P.map.mask >= 0;
+#define VM_PASS_VAR(V, PW)                                                                               \
+    if (MODE == MODE_PUSH_DEPOSIT && split) launch_pass_inst<K, V, MODE, (MODE == MODE_PUSH_DEPOSIT), PW>(ctx, pl, x, v, w, dcoef, out, P, F); \
+    else launch_pass_inst<K, V, MODE, false, PW>(ctx, pl, x, v, w, dcoef, out, P, F)
     switch (pl.var) {
-        case VAR_PRIV: launch_pass_inst<K, VAR_PRIV, MODE>(ctx, pl, x, v, w, dcoef, out, P, F); break;
-        case VAR_MATCH: launch_pass_inst<K, VAR_MATCH, MODE>(ctx, pl, x, v, w, dcoef, out, P, F); break;
-        default: launch_pass_inst<K, VAR_ATOMIC, MODE>(ctx, pl, x, v, w, dcoef, out, P, F); break;
+        case VAR_PRIV:
+            if (pow2) { VM_PASS_VAR(VAR_PRIV, true); } else { VM_PASS_VAR(VAR_PRIV, false); }
+            break;
+        case VAR_MATCH: VM_PASS_VAR(VAR_MATCH, false); break;
+        default: VM_PASS_VAR(VAR_ATOMIC, false); break;
     }
+#undef VM_PASS_VAR
 }
 
 template <int MODE>

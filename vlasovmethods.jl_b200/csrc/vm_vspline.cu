@@ -47,8 +47,9 @@ __device__ __forceinline__ void vdeposit_one(double vp, double wp, bool active, 
     double xi = 0.0;
     active = active && vcell_of(m, vp, c, xi);
     double val[K];
+    if (!active) wp = 0.0;
     if (c >= K - 1 && c <= m.ncell - K) {
-        bspline_uniform<K>(xi, val);                      // interior cell: uniform cardinal splines
+        bspline_uniform_w<K>(xi, wp, val);                // interior cell: uniform cardinal splines (x weight)
     } else {
         const double* A = cellpoly + (size_t)c * K * K;   // clamped end: exact polynomial pieces
 #pragma unroll
@@ -56,14 +57,8 @@ __device__ __forceinline__ void vdeposit_one(double vp, double wp, bool active, 
             double s = __ldg(A + j * K + K - 1);
 #pragma unroll
             for (int q = K - 2; q >= 0; --q) s = fma(s, xi, __ldg(A + j * K + q));
-            val[j] = s;
+            val[j] = s * wp;
         }
-    }
-#pragma unroll
-    for (int j = 0; j < K; ++j) val[j] *= wp;
-    if (!active) {
-#pragma unroll
-        for (int j = 0; j < K; ++j) val[j] = 0.0;
     }
     scatter<K, VAR>(wg, rep_log2, rep, lane, c, val, active);
 }
