@@ -39,9 +39,13 @@ def main():
     ap.add_argument("--what", default="deposit,lb,vp")
     ap.add_argument("--nh", default="16,64,128,256,512,1024")
     ap.add_argument("--orders", default="3,4,5")
+    ap.add_argument("--tune", default="", help="comma list of key=value tuning knobs (ctas_per_sm, threads_per_cta, replicas)")
     args = ap.parse_args()
     vm = load_package()
     ctx = vm.Context(0)
+    for kv in filter(None, args.tune.split(",")):
+        k, v = kv.split("=")
+        ctx.set_tuning(k, int(v))
     N = args.n
     L = 2 * math.pi / 0.3
     p = vm.DeviceParticles(ctx, N)
@@ -53,9 +57,9 @@ def main():
             for nh in [int(x) for x in args.nh.split(",")]:
                 fld = vm.DeviceField(ctx, 0.0, L, order, nh, 0)
                 if "deposit" in what:
-                    for mode, name in ((0, "deterministic"), (1, "atomic")):
+                    for mode, name in ((0, "deterministic"),) + ((() if args.tune else ((1, "atomic"),))):
                         ms = timed(ctx, lambda: fld.deposit(p, mode), 5)
-                        print(json.dumps({"kernel": "deposit", "mode": name, "order": order, "n_h": nh, "N": N, "ms": ms,
+                        print(json.dumps({"kernel": "deposit", "tune": args.tune, "mode": name, "order": order, "n_h": nh, "N": N, "ms": ms,
                                           "GBps": 16 * N / ms / 1e6, "frac_of_measured_peak": 16 * N / ms / 1e6 / PEAK}), flush=True)
                 if "vp" in what:
                     fld.run(p, 0.1, 3, 0, 0, 1.0)

@@ -236,6 +236,7 @@ int vm_ctx_set_tuning(vm_ctx* ctx, const char* key, int value)
         ctx->replicas = value;
     }
     else if (k == "profile") ctx->profile = value;
+    else if (k == "force_match") ctx->force_match = value;   // 1: MATCH.ANY grouping instead of xor rounds (A/B)
     else if (k == "no_pdl") ctx->no_pdl = value;     // 1: plain stream serialization for the pass kernels (A/B)
     else if (k == "no_fuse") ctx->no_fuse = value;   // 1: separate reduce/solve kernels even for small grids (A/B)
     else throw vm_error(VM_ERR_INVALID, "unknown tuning key: " + k);

@@ -8,7 +8,7 @@
 #pragma once
 #include "vm_internal.cuh"
 
-enum { VAR_PRIV = 0, VAR_MATCH = 1, VAR_ATOMIC = 2 };
+enum { VAR_PRIV = 0, VAR_MATCH = 1, VAR_ATOMIC = 2, VAR_XOR = 3 };
 
 // ---------------------------------------------------------------- scatter ---
 // Replica grids carry `ghost` extra rows after the n real ones, so a particle's K consecutive
@@ -25,6 +25,37 @@ __device__ __forceinline__ void scatter(double* __restrict__ wg, int rep_log2, i
         double* a = wg + (b0 << 5) + lane;
 #pragma unroll
         for (int j = 0; j < K; ++j) a[j * 32] += val[j];
+        return;
+    }
+    if (VAR == VAR_XOR) {
+        // R = 2^rep_log2 >= 4 replicas per warp: the 32/R lanes {l, l^R, l^2R, ...} share a replica column.
+        // Collisions inside such a group are found with 32/R - 1 xor-shuffle rounds of the cell index
+        // (cheaper than MATCH.ANY, whose cost grows with the number of distinct keys in the warp); the
+        // lowest colliding lane adds its peers' values in a fixed round order and does the plain RMW.
+        const int key = active ? b0 : ~lane;             // inactive lanes never match anybody
+        const int R = 1 << rep_log2;
+        double acc[K];
+#pragma unroll
+        for (int j = 0; j < K; ++j) acc[j] = val[j];
+        bool dead = false;
+        for (int d = R; d < 32; d += R) {                // warp-uniform trip count
+            const int pk = __shfl_xor_sync(VM_FULL_MASK, key, d);
+            const bool same = (pk == key);
+            if (same && ((lane ^ d) < lane)) dead = true;
+            if (__any_sync(VM_FULL_MASK, same)) {
+#pragma unroll
+                for (int j = 0; j < K; ++j) {
+                    const double t = __shfl_xor_sync(VM_FULL_MASK, val[j], d);
+                    if (same) acc[j] += t;
+                }
+            }
+        }
+        double* a = wg + (b0 << rep_log2) + rep;
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            if (!dead && active) a[j << rep_log2] += acc[j];
+            __syncwarp();
+        }
         return;
     }
     // group the lanes that target the same (cell, replica): in-warp sort-by-cell
@@ -250,10 +281,49 @@ struct DepositPlan {
 };
 
 // Choose CTA shape + replica count so that the replica grids fit in shared memory.
-inline DepositPlan plan_deposit(vm_ctx* ctx, int n_real, int ghost, int extra_doubles, int mode)
+// Measured on B200 (profiles/): the lane-private variant (32 replicas per warp, no collision handling)
+// beats the match-based variant by ~2.7x even when it only leaves room for 6-12 warps per SM, so it is
+// preferred whenever at least VM_PRIV_MIN_WARPS warps fit; otherwise the match variant runs with as many
+// replicas per warp as fit next to 32 resident warps.
+#define VM_PRIV_MIN_WARPS 6
+inline DepositPlan plan_deposit(vm_ctx* ctx, int n_real, int ghost, int extra_doubles, int mode,
+                                int priv_min_warps = VM_PRIV_MIN_WARPS)
 {
     const int sm = ctx->sm_count;
     const int n = n_real + ghost;   // rows per replica grid
+    const size_t sm_total = 227 * 1024;   // usable shared memory per SM on sm_100
+    auto budget_of = [&](int ctas) {
+        size_t b = sm_total / ctas - 1024;                   // 1 KB per-CTA system reservation
+        return b > ctx->smem_optin ? ctx->smem_optin : b;
+    };
+    auto fixed_of = [&](int threads) { return ((size_t)extra_doubles + (size_t)threads) * sizeof(double); };
+    const bool tuned = ctx->ctas_per_sm > 0 || ctx->threads_per_cta > 0 || ctx->replicas > 0;
+
+    if (mode != VM_DEPOSIT_ATOMIC && !tuned) {
+        // lane-private first: 2 CTAs x 16 warps if that fits, else one CTA with as many warps as fit
+        const size_t per_warp = (size_t)n * 32 * sizeof(double);
+        if (2 * (fixed_of(512) + 16 * per_warp) <= 2 * budget_of(2)) {
+            return DepositPlan{VAR_PRIV, 5, sm * 2, 512, fixed_of(512) + 16 * per_warp};
+        }
+        const size_t b1 = budget_of(1);
+        int warps = 32;
+        while (warps >= priv_min_warps && fixed_of(warps * 32) + warps * per_warp > b1) --warps;
+        if (warps >= priv_min_warps)
+            return DepositPlan{VAR_PRIV, 5, sm, warps * 32, fixed_of(warps * 32) + warps * per_warp};
+    }
+
+    if (mode != VM_DEPOSIT_ATOMIC && !tuned) {
+        // next best (measured): 16 or 8 replicas per warp with xor-shuffle collision handling, provided
+        // at least 24 warps stay resident; below that MATCH.ANY grouping with 32 warps wins again
+        for (int rl = 4; rl >= 3; --rl) {
+            const size_t per_warp = ((size_t)n << rl) * sizeof(double);
+            const size_t b1 = budget_of(1);
+            int warps = 32;
+            while (warps >= 24 && fixed_of(warps * 32) + warps * per_warp > b1) --warps;
+            if (warps >= 24) return DepositPlan{VAR_XOR, rl, sm, warps * 32, fixed_of(warps * 32) + warps * per_warp};
+        }
+    }
+
     struct Try { int ctas, threads; };
     std::vector<Try> tries;
     if (ctx->ctas_per_sm > 0 || ctx->threads_per_cta > 0) {
@@ -261,12 +331,10 @@ inline DepositPlan plan_deposit(vm_ctx* ctx, int n_real, int ghost, int extra_do
     } else {
         tries = {{2, 512}, {1, 512}, {1, 256}, {1, 128}, {1, 64}};
     }
-    const size_t sm_total = 227 * 1024;   // usable shared memory per SM on sm_100
     for (const Try& t : tries) {
         const int nwarps = t.threads / 32;
-        size_t budget = sm_total / t.ctas - 1024;            // 1 KB per-CTA system reservation
-        if (budget > ctx->smem_optin) budget = ctx->smem_optin;
-        const size_t fixed = ((size_t)extra_doubles + (size_t)t.threads) * sizeof(double);
+        const size_t budget = budget_of(t.ctas);
+        const size_t fixed = fixed_of(t.threads);
         if (budget <= fixed) continue;
         const size_t avail = (budget - fixed) / sizeof(double);
         DepositPlan pl{};
@@ -286,7 +354,7 @@ inline DepositPlan plan_deposit(vm_ctx* ctx, int n_real, int ghost, int extra_do
         if (ctx->replicas > 0) { rl = 0; while ((1 << rl) < ctx->replicas) ++rl; }
         while (rl > 0 && ((size_t)n << rl) > per_warp && ctx->replicas == 0) --rl;
         if (((size_t)n << rl) > per_warp) continue;
-        pl.var = (rl == 5) ? VAR_PRIV : VAR_MATCH;
+        pl.var = (rl == 5) ? VAR_PRIV : ((rl >= 3 && !ctx->force_match) ? VAR_XOR : VAR_MATCH);
         pl.rep_log2 = rl;
         pl.smem = fixed + ((size_t)n << rl) * nwarps * sizeof(double);
         return pl;

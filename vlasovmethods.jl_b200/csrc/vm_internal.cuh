@@ -47,7 +47,7 @@ struct vm_ctx {
     unsigned long long launches = 0;
     cudaEvent_t events[VM_MAX_EVENTS] = {};
     // tuning (0 = auto)
-    int ctas_per_sm = 0, threads_per_cta = 0, replicas = 0, profile = 0, no_fuse = 0, no_pdl = 0;
+    int ctas_per_sm = 0, threads_per_cta = 0, replicas = 0, profile = 0, no_fuse = 0, no_pdl = 0, force_match = 0;
     // per-launch event brackets of the dominant kernel (profile == 1)
     std::vector<cudaEvent_t> prof_events;   // pairs: [2i] start, [2i+1] stop
     size_t prof_used = 0;                    // events in use since the last read

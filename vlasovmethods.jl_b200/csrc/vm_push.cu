@@ -372,6 +372,7 @@ void launch_pass_var(vm_ctx* ctx, const DepositPlan& pl, double* x, double* v, c
             if (pow2) { VM_PASS_VAR(VAR_PRIV, true); } else { VM_PASS_VAR(VAR_PRIV, false); }
             break;
         case VAR_MATCH: VM_PASS_VAR(VAR_MATCH, false); break;
+        case VAR_XOR: VM_PASS_VAR(VAR_XOR, false); break;
         default: VM_PASS_VAR(VAR_ATOMIC, false); break;
     }
 #undef VM_PASS_VAR
@@ -458,7 +459,9 @@ static void pass_with_deposit(vm_field* f, vm_particles* p, int pass_mode, int d
     vm_ctx* ctx = f->ctx;
     const int n = f->n;
     const int ncols = n;   // partial rows hold the grid only (the K/M sums live in their own rows)
-    DepositPlan pl = plan_deposit(ctx, n, f->order - 1, pass_mode == MODE_PUSH_DEPOSIT ? n + f->order : 0, deposit_mode);
+    // the 32-40 B/particle passes need more resident warps than the deposit-only pass (measured)
+    DepositPlan pl = plan_deposit(ctx, n, f->order - 1, pass_mode == MODE_PUSH_DEPOSIT ? n + f->order : 0, deposit_mode,
+                                  pass_mode == MODE_DEPOSIT ? VM_PRIV_MIN_WARPS : 12);
     P.map = f->map;
     P.n = p->n;
     P.rep_log2 = pl.rep_log2;

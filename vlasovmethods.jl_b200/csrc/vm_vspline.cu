@@ -399,6 +399,7 @@ void launch_vdep_var(vm_vspline* s, const DepositPlan& pl, const double* v, cons
     switch (pl.var) {
         case VAR_PRIV: launch_vdep_inst<K, VAR_PRIV>(s, pl, v, w, np, out, F); break;
         case VAR_MATCH: launch_vdep_inst<K, VAR_MATCH>(s, pl, v, w, np, out, F); break;
+        case VAR_XOR: launch_vdep_inst<K, VAR_XOR>(s, pl, v, w, np, out, F); break;
         default: launch_vdep_inst<K, VAR_ATOMIC>(s, pl, v, w, np, out, F); break;
     }
 }
