@@ -322,6 +322,44 @@ def test_clb_rk438_matches_oracle_and_conserves(vm, oracle, ctx, rng):
             assert abs(diag[-1, 2] - diag[0, 2]) / diag[0, 2] <= 1e-6
 
 
+def test_rk438_fused_equals_unfused_bitwise(vm, rng):
+    """The fused stage pass (RHS + stage assembly + next deposit) must reproduce the kernel-per-operation
+    driver bit for bit (same arithmetic, same deterministic deposit)."""
+    a, b, nknots, k = -10.0, 10.0, 41, 4
+    npart = 50001
+    v = np.concatenate([rng.standard_normal(npart // 2) + 2.0, rng.standard_normal(npart - npart // 2) - 2.0])
+    w = np.full(npart, 1.0 / npart)
+    res = {}
+    for no_fuse in (0, 1):
+        c = vm.Context(0)
+        c.set_tuning("no_fuse", no_fuse)
+        vs = vm.DeviceVSpline(c, a, b, nknots, k, 1)
+        p = vm.DeviceParticles(c, npart)
+        for cons in (True, False):
+            p.upload(np.zeros(npart), v, w)
+            vs.rk438_run(p, 1e-2, 3, 1.0, cons, 0)
+            res[(no_fuse, cons)] = p.download(x=False, w=False)[1].copy()
+        vs.close(); p.close(); c.close()
+    for cons in (True, False):
+        assert np.array_equal(res[(0, cons)], res[(1, cons)]), cons
+
+
+def test_vp_run_bitwise_reproducible(vm, ctx, rng):
+    """Deterministic deposit => the whole fused time loop is bit-reproducible run to run."""
+    a, b, n, k = 0.0, 2 * math.pi / 0.3, 16, 4
+    npart = 200001
+    x = rng.uniform(a, b, npart); v = rng.standard_normal(npart); w = np.full(npart, (b - a) / npart)
+    fld = vm.DeviceField(ctx, a, b, k, n, 0)
+    p = vm.DeviceParticles(ctx, npart)
+    outs = []
+    for _ in range(3):
+        p.upload(x, v, w)
+        d = fld.run(p, 0.1, 10, 5, 0, 1.0)
+        xs, vs_, _ = p.download(w=False)
+        outs.append((xs.tobytes(), vs_.tobytes(), d.tobytes(), fld.coefficients.tobytes()))
+    assert outs[0] == outs[1] == outs[2]
+
+
 def test_mirror_lenard_bernstein(vm, oracle, ctx, rng):
     vm.set_default_context(ctx)
     npart = 1000

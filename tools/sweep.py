@@ -39,6 +39,7 @@ def main():
     ap.add_argument("--what", default="deposit,lb,vp")
     ap.add_argument("--nh", default="16,64,128,256,512,1024")
     ap.add_argument("--orders", default="3,4,5")
+    ap.add_argument("--nknots", default="41,129,513")
     ap.add_argument("--tune", default="", help="comma list of key=value tuning knobs (ctas_per_sm, threads_per_cta, replicas)")
     args = ap.parse_args()
     vm = load_package()
@@ -73,7 +74,7 @@ def main():
 
     if "lb" in what:
         p.fill(vm._lib.VM_FILL_DOUBLE_MAXWELLIAN, [-10.0, 10.0, 2.0], 2)
-        for nknots in (41, 129, 513):
+        for nknots in [int(k) for k in args.nknots.split(",")]:
             vs = vm.DeviceVSpline(ctx, -10.0, 10.0, nknots, 4, 1)
             for cons in (False, True):
                 ms = timed(ctx, lambda: vs.lb_rhs(p, 1.0, cons, to_host=False), 5)
@@ -81,9 +82,12 @@ def main():
                 print(json.dumps({"kernel": "clb_rhs" if cons else "lb_rhs", "nknots": nknots, "N": N, "ms": ms,
                                   "rhs_evals_per_s": N / ms * 1e3, "GBps": alg * N / ms / 1e6,
                                   "frac_of_measured_peak": alg * N / ms / 1e6 / PEAK}), flush=True)
-            ms = timed(ctx, lambda: vs.rk438_run(p, 1e-3, 1, 1.0, True, 0), 3)
-            print(json.dumps({"kernel": "clb_rk438_step", "nknots": nknots, "N": N, "ms_per_step": ms,
-                              "particle_steps_per_s": N / ms * 1e3}), flush=True)
+            for cons in (False, True):
+                ms = timed(ctx, lambda: vs.rk438_run(p, 1e-3, 5, 1.0, cons, 0), 2) / 5
+                alg = 200 if cons else 144
+                print(json.dumps({"kernel": ("clb" if cons else "lb") + "_rk438_step", "nknots": nknots, "N": N, "ms_per_step": ms,
+                                  "particle_steps_per_s": N / ms * 1e3, "GBps": alg * N / ms / 1e6,
+                                  "frac_of_measured_peak": alg * N / ms / 1e6 / PEAK}), flush=True)
             vs.close()
 
 

@@ -164,6 +164,107 @@ __device__ __forceinline__ void eval_f_df(const double* __restrict__ psh, const 
     df = (K > 1) ? sd * m.inv_h : 0.0;
 }
 
+// ------------------------------------------------ fused RK438 stage pass ----
+// One pass per Runge-Kutta stage of the Lenard-Bernstein velocity ODE
+//   q_s    = v + dt (a1 k1 + a2 k2 + a3 k3)                      (stage state, recomputed, never re-read)
+//   k_s    = -nu (f_s'(q_s) + (A1 + A2 q_s) f_s(q_s))             (LB_rhs! / CLB_rhs!)
+//   q_next = v + dt (c1 k1 + c2 k2 + c3 k3 + cs k_s)              (next stage state, or v_new on the last stage)
+//   deposit w * phi_i(q_next)                                      (projection for the next right-hand side)
+// i.e. RHS evaluation, stage assembly and the next projection's deposit in ONE sweep over the particles
+// (LB: 144 B/particle per RK438 step instead of 304 B for separate kernels).  Same arithmetic as
+// k_v_rhs + k_rk_combine + k_v_deposit, so the fused and unfused drivers agree bitwise.
+struct StageParams {
+    const double *k1, *k2, *k3;
+    double a1, a2, a3;
+    double c1, c2, c3, cs;
+    double* kout;      // k_s, or nullptr on the last stage
+    double* qout;      // q_next for the moments pass (nullptr: not needed); on the last stage this is v itself
+    double dt, nu;
+};
+
+template <int K, int VAR>
+__global__ void __launch_bounds__(1024, 1)
+k_lb_stage(const double* v, const double* __restrict__ w, long np, VCell m, const double* __restrict__ cellpoly,
+           const double* __restrict__ poly, const double* __restrict__ mom, const StageParams S, int npar, int rep_log2,
+           double* __restrict__ out, const FinishParams F)
+{
+    extern __shared__ double smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int npoly = m.ncell * K;
+    double* psh = smem;
+    double* grid = smem + npoly;
+    const int gsz = npar << rep_log2;
+    const int gtotal = (VAR == VAR_ATOMIC) ? gsz : gsz * nwarps;
+    double* scratch = grid + gtotal;
+    for (int i = threadIdx.x; i < gtotal; i += blockDim.x) grid[i] = 0.0;
+    for (int i = threadIdx.x; i < npoly; i += blockDim.x) psh[i] = poly[i];
+    __syncthreads();
+    double* wg = (VAR == VAR_ATOMIC) ? grid : grid + warp * gsz;
+    const int rep = ((VAR == VAR_ATOMIC) ? warp : lane) & ((1 << rep_log2) - 1);
+    const double A1 = mom[5], A2 = mom[6];
+
+    auto one = [&](double vp, double wp, double k1, double k2, double k3, bool active, double& ks, double& qn) {
+        double q = vp;
+        if (S.k1) {
+            double t = S.a1 * k1;
+            if (S.k2) t = fma(S.a2, k2, t);
+            if (S.k3) t = fma(S.a3, k3, t);
+            q = fma(S.dt, t, vp);
+        }
+        double f, df;
+        eval_f_df<K>(psh, m, q, f, df);
+        ks = -S.nu * (df + fma(A2, q, A1) * f);
+        double t;
+        if (S.k1) {
+            t = S.c1 * k1;
+            if (S.k2) t = fma(S.c2, k2, t);
+            if (S.k3) t = fma(S.c3, k3, t);
+            t = fma(S.cs, ks, t);
+        } else {
+            t = S.cs * ks;
+        }
+        qn = fma(S.dt, t, vp);
+        vdeposit_one<K, VAR>(qn, wp, active, m, cellpoly, wg, npar, rep_log2, rep, lane);
+    };
+
+    const long npairs = np >> 1;
+    const long stride = (long)gridDim.x * blockDim.x;
+    const long gtid = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long iters = (npairs + stride - 1) / stride;    // uniform trip count (warp-collective scatter variants)
+    for (long it = 0; it < iters; ++it) {
+        const long q = it * stride + gtid;
+        const bool active = q < npairs;
+        double2 vv = make_double2(0., 0.), ww = vv, a = vv, b = vv, c = vv;
+        if (active) {
+            vv = ld_stream2(v + 2 * q);
+            ww = ld_stream2(w + 2 * q);
+            if (S.k1) a = ld_stream2(S.k1 + 2 * q);
+            if (S.k2) b = ld_stream2(S.k2 + 2 * q);
+            if (S.k3) c = ld_stream2(S.k3 + 2 * q);
+        }
+        double2 ks, qn;
+        one(vv.x, ww.x, a.x, b.x, c.x, active, ks.x, qn.x);
+        one(vv.y, ww.y, a.y, b.y, c.y, active, ks.y, qn.y);
+        if (active) {
+            if (S.kout) st_stream2(S.kout + 2 * q, ks);
+            if (S.qout) st_stream2(S.qout + 2 * q, qn);
+        }
+    }
+    if ((np & 1) && blockIdx.x == 0 && warp == 0) {
+        const bool active = (lane == 0);
+        const long p = np - 1;
+        double ks = 0., qn = 0.;
+        one(active ? v[p] : 0.0, active ? w[p] : 0.0, (active && S.k1) ? S.k1[p] : 0.0, (active && S.k2) ? S.k2[p] : 0.0,
+            (active && S.k3) ? S.k3[p] : 0.0, active, ks, qn);
+        if (active) {
+            if (S.kout) S.kout[p] = ks;
+            if (S.qout) S.qout[p] = qn;
+        }
+    }
+    flush_grid<VAR>(grid, scratch, out, npar, 0, rep_log2, nwarps, npar);
+    if (VAR != VAR_ATOMIC && F.mode != FINISH_NONE) finish_last_cta(F, out, gridDim.x, npar, grid, scratch);
+}
+
 // Streaming helper: each thread handles U pairs (4 particles for U = 2) per iteration, all loads issued
 // before any use, so that enough bytes are in flight for these low-byte passes.
 #define VM_STREAM_PAIRS 2
@@ -414,23 +515,33 @@ void launch_vdep_var(vm_vspline* s, const DepositPlan& pl, const double* v, cons
         default: throw vm_error(VM_ERR_UNSUPPORTED, "spline order must be in 2..6");        \
     }
 
-// projection: deposit -> fixed-order reduce -> all-reduce -> M^{-1} -> per-cell polynomials
-void project_dev(vm_vspline* s, const double* v, const double* w, long np)
+// plan + finish parameters shared by the projection deposit and the fused RK stage pass
+struct VDepSetup {
+    DepositPlan pl;
+    FinishParams F;
+    double* out;
+};
+
+VDepSetup vdep_setup(vm_vspline* s, int extra_doubles)
 {
     vm_ctx* ctx = s->ctx;
-    DepositPlan pl = plan_deposit(ctx, s->npar, 0, 0, VM_DEPOSIT_DETERMINISTIC);
-    double* out = vm_partials(ctx, (size_t)pl.grid * s->npar);
-    FinishParams F{};
-    const size_t gdoubles = ((size_t)s->npar << pl.rep_log2) * (size_t)(pl.threads / 32);
-    if (s->npar <= VM_FUSE_MAX_N && !ctx->no_fuse && pl.var != VAR_ATOMIC && gdoubles >= (size_t)2 * s->npar + 1) {
-        F.mode = FINISH_REDUCE;           // last CTA sums the per-CTA rows in a fixed order
-        F.ticket = ctx->ticket;
-        F.rhs = s->rhs;
+    VDepSetup d{};
+    d.pl = plan_deposit(ctx, s->npar, 0, extra_doubles, VM_DEPOSIT_DETERMINISTIC);
+    d.out = vm_partials(ctx, (size_t)d.pl.grid * s->npar);
+    const size_t gdoubles = ((size_t)s->npar << d.pl.rep_log2) * (size_t)(d.pl.threads / 32);
+    if (s->npar <= VM_FUSE_MAX_N && !ctx->no_fuse && d.pl.var != VAR_ATOMIC && gdoubles >= (size_t)2 * s->npar + 1) {
+        d.F.mode = FINISH_REDUCE;           // last CTA sums the per-CTA rows in a fixed order
+        d.F.ticket = ctx->ticket;
+        d.F.rhs = s->rhs;
     }
-    vm_prof_mark(ctx);
-    VM_ORDER_SWITCH(s->order, launch_vdep_var<K>(s, pl, v, w, np, out, F));
-    vm_prof_mark(ctx);
-    if (F.mode == FINISH_NONE) vm_reduce_rows(ctx, out, pl.grid, s->npar, s->rhs);
+    return d;
+}
+
+// rows (or the fused reduction) -> all-reduce -> M^{-1} -> per-cell polynomials
+void after_deposit(vm_vspline* s, const VDepSetup& d)
+{
+    vm_ctx* ctx = s->ctx;
+    if (d.F.mode == FINISH_NONE) vm_reduce_rows(ctx, d.out, d.pl.grid, s->npar, s->rhs);
     vm_allreduce_sum(ctx, s->rhs, (size_t)s->npar);
     const int off = s->bc ? 1 : 0;
     k_v_solve<<<(s->nv + 7) / 8, 256, 0, ctx->stream>>>(s->minv, s->rhs, s->nv, off, s->npar, s->coef);
@@ -438,6 +549,43 @@ void project_dev(vm_vspline* s, const double* v, const double* w, long np)
     const int tot = s->ncell * s->order;
     k_v_poly<<<(tot + 255) / 256, 256, 0, ctx->stream>>>(s->coef, s->cellpoly, s->ncell, s->order, s->poly);
     VM_LAUNCHED(ctx);
+}
+
+// projection: deposit -> fixed-order reduce -> all-reduce -> M^{-1} -> per-cell polynomials
+void project_dev(vm_vspline* s, const double* v, const double* w, long np)
+{
+    vm_ctx* ctx = s->ctx;
+    VDepSetup d = vdep_setup(s, 0);
+    vm_prof_mark(ctx);
+    VM_ORDER_SWITCH(s->order, launch_vdep_var<K>(s, d.pl, v, w, np, d.out, d.F));
+    vm_prof_mark(ctx);
+    after_deposit(s, d);
+}
+
+template <int K, int VAR>
+void launch_stage_inst(vm_vspline* s, const VDepSetup& d, const double* v, const double* w, long np, const StageParams& S)
+{
+    vm_ctx* ctx = s->ctx;
+    static size_t configured[64] = {};
+    size_t& conf = configured[ctx->device & 63];
+    if (d.pl.smem > conf) {
+        VM_CUDA(cudaFuncSetAttribute(k_lb_stage<K, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d.pl.smem));
+        conf = d.pl.smem;
+    }
+    k_lb_stage<K, VAR><<<d.pl.grid, d.pl.threads, d.pl.smem, ctx->stream>>>(v, w, np, vcell(s), s->cellpoly, s->poly,
+                                                                         s->moments, S, s->npar, d.pl.rep_log2, d.out, d.F);
+    VM_LAUNCHED(ctx);
+}
+
+template <int K>
+void launch_stage(vm_vspline* s, const VDepSetup& d, const double* v, const double* w, long np, const StageParams& S)
+{
+    switch (d.pl.var) {
+        case VAR_PRIV: launch_stage_inst<K, VAR_PRIV>(s, d, v, w, np, S); break;
+        case VAR_MATCH: launch_stage_inst<K, VAR_MATCH>(s, d, v, w, np, S); break;
+        case VAR_XOR: launch_stage_inst<K, VAR_XOR>(s, d, v, w, np, S); break;
+        default: launch_stage_inst<K, VAR_ATOMIC>(s, d, v, w, np, S); break;
+    }
 }
 
 void moments_dev(vm_vspline* s, const double* v, long np, int conservative)
@@ -702,24 +850,55 @@ int vm_lb_rk438_run(vm_vspline* s, vm_particles* p, double dt, int nsteps, doubl
     };
     if (nrows > 0) record(0.0);
     if (np > 0 && nsteps > 0) {
-        double *k1 = work_array(p, 0), *k2 = work_array(p, 1), *k3 = work_array(p, 2), *k4 = work_array(p, 3),
-               *q = work_array(p, 4);
+        double *k1 = work_array(p, 0), *k2 = work_array(p, 1), *k3 = work_array(p, 2), *q = work_array(p, 4);
         // classical 3/8 rule (GeometricIntegrators RK438): a21=1/3; a31=-1/3, a32=1; a41=1, a42=-1, a43=1
         const double a21 = 1.0 / 3.0, a31 = -1.0 / 3.0;
-        for (int st = 1; st <= nsteps; ++st) {
-            rhs_dev(s, p->v, p->w, np, nu, conservative, k1);
-            k_rk_combine<<<grid, threads, 0, ctx->stream>>>(p->v, k1, nullptr, nullptr, nullptr, a21, 0, 0, 0, dt, np, q);
-            VM_LAUNCHED(ctx);
-            rhs_dev(s, q, p->w, np, nu, conservative, k2);
-            k_rk_combine<<<grid, threads, 0, ctx->stream>>>(p->v, k1, k2, nullptr, nullptr, a31, 1.0, 0, 0, dt, np, q);
-            VM_LAUNCHED(ctx);
-            rhs_dev(s, q, p->w, np, nu, conservative, k3);
-            k_rk_combine<<<grid, threads, 0, ctx->stream>>>(p->v, k1, k2, k3, nullptr, 1.0, -1.0, 1.0, 0, dt, np, q);
-            VM_LAUNCHED(ctx);
-            rhs_dev(s, q, p->w, np, nu, conservative, k4);
-            k_rk_combine<<<grid, threads, 0, ctx->stream>>>(p->v, k1, k2, k3, k4, 0.125, 0.375, 0.375, 0.125, dt, np, p->v);
-            VM_LAUNCHED(ctx);
-            if (diag_every > 0 && st % diag_every == 0) record(dt * st);
+        if (ctx->no_fuse) {
+            // reference-shaped driver: separate projection / moments / RHS / stage-assembly kernels
+            double* k4 = work_array(p, 3);
+            for (int st = 1; st <= nsteps; ++st) {
+                rhs_dev(s, p->v, p->w, np, nu, conservative, k1);
+                k_rk_combine<<<grid, threads, 0, ctx->stream>>>(p->v, k1, nullptr, nullptr, nullptr, a21, 0, 0, 0, dt, np, q);
+                VM_LAUNCHED(ctx);
+                rhs_dev(s, q, p->w, np, nu, conservative, k2);
+                k_rk_combine<<<grid, threads, 0, ctx->stream>>>(p->v, k1, k2, nullptr, nullptr, a31, 1.0, 0, 0, dt, np, q);
+                VM_LAUNCHED(ctx);
+                rhs_dev(s, q, p->w, np, nu, conservative, k3);
+                k_rk_combine<<<grid, threads, 0, ctx->stream>>>(p->v, k1, k2, k3, nullptr, 1.0, -1.0, 1.0, 0, dt, np, q);
+                VM_LAUNCHED(ctx);
+                rhs_dev(s, q, p->w, np, nu, conservative, k4);
+                k_rk_combine<<<grid, threads, 0, ctx->stream>>>(p->v, k1, k2, k3, k4, 0.125, 0.375, 0.375, 0.125, dt, np, p->v);
+                VM_LAUNCHED(ctx);
+                if (diag_every > 0 && st % diag_every == 0) record(dt * st);
+            }
+        } else {
+            // fused driver: one particle pass per stage (RHS + stage assembly + next projection's deposit),
+            // plus the 8 B/particle moments pass for the conservative operator
+            project_dev(s, p->v, p->w, np);
+            moments_dev(s, p->v, np, conservative);
+            const size_t extra = (size_t)s->ncell * s->order;    // polynomial table lives in shared memory too
+            auto stage = [&](const double* pk1, const double* pk2, const double* pk3, double a1, double a2, double a3,
+                             double c1, double c2, double c3, double cs, double* kout, double* qout) {
+                StageParams S{};
+                S.k1 = pk1; S.k2 = pk2; S.k3 = pk3;
+                S.a1 = a1; S.a2 = a2; S.a3 = a3;
+                S.c1 = c1; S.c2 = c2; S.c3 = c3; S.cs = cs;
+                S.kout = kout; S.dt = dt; S.nu = nu;
+                S.qout = (conservative || qout == p->v) ? qout : nullptr;   // LB needs no stored stage state
+                VDepSetup d = vdep_setup(s, (int)extra);
+                vm_prof_mark(ctx);
+                VM_ORDER_SWITCH(s->order, launch_stage<K>(s, d, p->v, p->w, np, S));
+                vm_prof_mark(ctx);
+                after_deposit(s, d);
+                moments_dev(s, qout, np, conservative);
+            };
+            for (int st = 1; st <= nsteps; ++st) {
+                stage(nullptr, nullptr, nullptr, 0, 0, 0, 0, 0, 0, a21, k1, q);                    // k1, q2
+                stage(k1, nullptr, nullptr, a21, 0, 0, a31, 0, 0, 1.0, k2, q);                      // k2, q3
+                stage(k1, k2, nullptr, a31, 1.0, 0, 1.0, -1.0, 0, 1.0, k3, q);                      // k3, q4
+                stage(k1, k2, k3, 1.0, -1.0, 1.0, 0.125, 0.375, 0.375, 0.125, nullptr, p->v);       // v_new (+ its projection)
+                if (diag_every > 0 && st % diag_every == 0) record(dt * st);
+            }
         }
     }
     if (nrows > 0) {
