@@ -1,0 +1,105 @@
+"""Full-size checks at the BASELINE.json configuration sizes (1e8 / 1e7 particles) through
+size-independent properties, plus an oracle comparison where the CPU oracle finishes in seconds."""
+import math
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+N_BIG = 100_000_000
+
+
+@pytest.fixture(scope="module")
+def ctx(vm):
+    c = vm.Context(0)
+    info = c.device_info()
+    if info["free_bytes"] < 12e9:
+        pytest.skip("not enough free device memory for the 1e8-particle checks")
+    yield c
+    c.close()
+
+
+def test_bump_on_tail_1e8_properties(vm, ctx):
+    """configs[1]: bump-on-tail, 1e8 particles, n_h = 16, cubic."""
+    L = 2 * math.pi / 0.3
+    fld = vm.DeviceField(ctx, 0.0, L, 4, 16, 0)
+    p = vm.DeviceParticles(ctx, N_BIG)
+    p.fill(vm._lib.VM_FILL_BUMP_ON_TAIL, [0.03, 0.3, 0.1, 0.5, 4.5], 20240601)
+    # partition of unity: sum_i rhs_i == sum_p w_p == L
+    fld.deposit(p, 0)
+    rhs = fld.rhs
+    assert abs(rhs.sum() - L) <= 1e-12 * L
+    # density 1 - eps cos(kappa x): rhs against the exact Galerkin moments of that density
+    assert np.all(rhs > 0) and abs(rhs.max() / rhs.min() - (1 + 0.03) / (1 - 0.03)) < 2e-2
+    # bitwise reproducible and independent of the deposit variant to rounding
+    b0 = rhs.tobytes()
+    fld.deposit(p, 0)
+    assert fld.rhs.tobytes() == b0
+    fld.deposit(p, 1)
+    assert np.max(np.abs(fld.rhs - rhs)) <= 1e-12 * rhs.max()
+    # solve: S phi = rhs - mean, gauge sum(phi) = 0
+    fld.deposit(p, 0); fld.solve()
+    phi = fld.coefficients
+    S = fld.stiffness_matrix()
+    assert np.max(np.abs(S @ phi - (rhs - rhs.mean()))) <= 1e-12 * np.max(np.abs(rhs - rhs.mean()))
+    assert abs(phi.sum()) <= 1e-12 * np.abs(phi).sum()
+    # time loop: total energy drift of the variational scheme stays tiny; histories are reproducible
+    d1 = fld.run(p, 0.1, 20, 5, 0, 1.0)
+    E = d1[:, 0] + d1[:, 1]
+    assert np.all(np.isfinite(d1)) and np.max(np.abs(E - E[0])) / E[0] < 1e-5
+    assert abs(d1[-1, 3] - L) <= 1e-12 * L
+    p.fill(vm._lib.VM_FILL_BUMP_ON_TAIL, [0.03, 0.3, 0.1, 0.5, 4.5], 20240601)
+    d2 = fld.run(p, 0.1, 20, 5, 0, 1.0)
+    assert d1.tobytes() == d2.tobytes()
+    # unfused passes give the same histories to rounding
+    p.fill(vm._lib.VM_FILL_BUMP_ON_TAIL, [0.03, 0.3, 0.1, 0.5, 4.5], 20240601)
+    d3 = fld.run(p, 0.1, 20, 5, vm._lib.VM_RUN_UNFUSED, 1.0)
+    assert np.allclose(d3, d1, rtol=1e-10, atol=1e-12)
+    p.close(); fld.close()
+
+
+def test_clb_1e8_conservation(vm, ctx):
+    """configs[3]: conservative Lenard-Bernstein, 1e8 particles: sum vdot = 0 and sum v vdot = 0 by construction."""
+    vs = vm.DeviceVSpline(ctx, -10.0, 10.0, 41, 4, 1)
+    p = vm.DeviceParticles(ctx, N_BIG)
+    p.fill(vm._lib.VM_FILL_DOUBLE_MAXWELLIAN, [-10.0, 10.0, 2.0], 7)
+    vdot = vs.lb_rhs(p, 1.0, True)
+    v = p.download(x=False, w=False)[1]
+    scale = np.abs(vdot).sum()
+    assert abs(vdot.sum()) <= 1e-9 * scale
+    assert abs(np.dot(v, vdot)) <= 1e-9 * np.abs(v * vdot).sum()
+    m5, A = vs.moments(p)
+    f, df = vs.eval(v[:200000])
+    assert abs(m5[0] / N_BIG - f.mean()) < 5e-3 * abs(f.mean())
+    # RK438 steps: momentum and energy of the particle set are conserved (script diagnostics, :49-50,64)
+    diag = vs.rk438_run(p, 1e-2, 3, 1.0, True, 1)
+    assert abs(diag[-1, 1] - diag[0, 1]) <= 1e-7 * N_BIG
+    assert abs(diag[-1, 2] - diag[0, 2]) / diag[0, 2] <= 1e-7
+    p.close(); vs.close()
+
+
+def test_lb_1e7_matches_oracle(vm, oracle, ctx):
+    """configs[2]: Lenard-Bernstein relaxation, 1e7 particles, 41 knots, order 4: full oracle comparison."""
+    n = 10_000_000
+    a, b, nknots, k = -10.0, 10.0, 41, 4
+    vs = vm.DeviceVSpline(ctx, a, b, nknots, k, 1)
+    p = vm.DeviceParticles(ctx, n)
+    p.fill(vm._lib.VM_FILL_NORMAL, [0.0, 1.0], 11)
+    _, v, w = p.download()
+    M = oracle.dirichlet_mass(a, b, nknots, k)
+    vs.project(p)
+    coef, rhs = oracle.vproject(v, w, a, b, nknots, k, M)
+    assert np.max(np.abs(vs.rhs - rhs)) <= 1e-12 * np.max(np.abs(rhs))
+    assert np.max(np.abs(vs.coefficients - coef)) <= 1e-11 * np.max(np.abs(coef))
+    sub = slice(0, 200000)
+    for cons in (False, True):
+        vdot = vs.lb_rhs(p, 1.0, cons)
+        f, df = oracle.vspline_eval(v[sub], a, b, nknots, k, coef)
+        if cons:
+            A1, A2 = oracle.clb_coefficients(oracle.vmoments(v, a, b, nknots, k, coef))
+        else:
+            A1, A2 = 0.0, 1.0
+        ref = -(df + (A1 + A2 * v[sub]) * f)
+        assert np.max(np.abs(vdot[sub] - ref)) <= 1e-9 * np.max(np.abs(ref)), cons
+    p.close(); vs.close()
