@@ -145,6 +145,18 @@ __global__ void k_v_poly(const double* __restrict__ coef_par, const double* __re
     }
 }
 
+// The per-cell polynomial table sits in shared memory with an ODD row stride (K | 1 doubles): rows of
+// 16 consecutive cells then start in 16 distinct bank pairs, so a warp whose lanes sit in different cells
+// reads its coefficients without bank conflicts (28 % of the shared wavefronts were conflicts at stride K).
+template <int K>
+struct PolyRow { static constexpr int stride = K | 1; };
+
+template <int K>
+__device__ __forceinline__ void load_poly(double* __restrict__ psh, const double* __restrict__ poly, int ncell)
+{
+    for (int i = threadIdx.x; i < ncell * K; i += blockDim.x) psh[(i / K) * PolyRow<K>::stride + (i % K)] = poly[i];
+}
+
 template <int K>
 __device__ __forceinline__ void eval_f_df(const double* __restrict__ psh, const VCell& m, double v, double& f, double& df)
 {
@@ -153,7 +165,7 @@ __device__ __forceinline__ void eval_f_df(const double* __restrict__ psh, const 
     f = 0.0;
     df = 0.0;
     if (!vcell_of(m, v, c, xi)) return;
-    const double* q = psh + c * K;
+    const double* q = psh + c * PolyRow<K>::stride;
     double sf = q[K - 1], sd = (double)(K - 1) * q[K - 1];
 #pragma unroll
     for (int j = K - 2; j >= 0; --j) {
@@ -182,7 +194,7 @@ struct StageParams {
     double dt, nu;
 };
 
-template <int K, int VAR>
+template <int K, int VAR, int STAGE>
 __global__ void __launch_bounds__(1024, 1)
 k_lb_stage(const double* v, const double* __restrict__ w, long np, VCell m, const double* __restrict__ cellpoly,
            const double* __restrict__ poly, const double* __restrict__ mom, const StageParams S, int npar, int rep_log2,
@@ -190,35 +202,36 @@ k_lb_stage(const double* v, const double* __restrict__ w, long np, VCell m, cons
 {
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    const int npoly = m.ncell * K;
+    const int npoly = m.ncell * PolyRow<K>::stride;
     double* psh = smem;
     double* grid = smem + npoly;
     const int gsz = npar << rep_log2;
-    const int gtotal = (VAR == VAR_ATOMIC) ? gsz : gsz * nwarps;
+    const int gtotal = gsz * nwarps;
     double* scratch = grid + gtotal;
     for (int i = threadIdx.x; i < gtotal; i += blockDim.x) grid[i] = 0.0;
-    for (int i = threadIdx.x; i < npoly; i += blockDim.x) psh[i] = poly[i];
+    load_poly<K>(psh, poly, m.ncell);
     __syncthreads();
-    double* wg = (VAR == VAR_ATOMIC) ? grid : grid + warp * gsz;
-    const int rep = ((VAR == VAR_ATOMIC) ? warp : lane) & ((1 << rep_log2) - 1);
+    double* wg = grid + warp * gsz;
+    const int rep = lane & ((1 << rep_log2) - 1);
     const double A1 = mom[5], A2 = mom[6];
 
+    // STAGE s uses k_1 .. k_{s-1} (compile time): no pointer tests in the particle loop
     auto one = [&](double vp, double wp, double k1, double k2, double k3, bool active, double& ks, double& qn) {
         double q = vp;
-        if (S.k1) {
+        if (STAGE >= 2) {
             double t = S.a1 * k1;
-            if (S.k2) t = fma(S.a2, k2, t);
-            if (S.k3) t = fma(S.a3, k3, t);
+            if (STAGE >= 3) t = fma(S.a2, k2, t);
+            if (STAGE >= 4) t = fma(S.a3, k3, t);
             q = fma(S.dt, t, vp);
         }
         double f, df;
         eval_f_df<K>(psh, m, q, f, df);
         ks = -S.nu * (df + fma(A2, q, A1) * f);
         double t;
-        if (S.k1) {
+        if (STAGE >= 2) {
             t = S.c1 * k1;
-            if (S.k2) t = fma(S.c2, k2, t);
-            if (S.k3) t = fma(S.c3, k3, t);
+            if (STAGE >= 3) t = fma(S.c2, k2, t);
+            if (STAGE >= 4) t = fma(S.c3, k3, t);
             t = fma(S.cs, ks, t);
         } else {
             t = S.cs * ks;
@@ -227,42 +240,42 @@ k_lb_stage(const double* v, const double* __restrict__ w, long np, VCell m, cons
         vdeposit_one<K, VAR>(qn, wp, active, m, cellpoly, wg, npar, rep_log2, rep, lane);
     };
 
-    const long npairs = np >> 1;
-    const long stride = (long)gridDim.x * blockDim.x;
-    const long gtid = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long iters = (npairs + stride - 1) / stride;    // uniform trip count (warp-collective scatter variants)
-    for (long it = 0; it < iters; ++it) {
-        const long q = it * stride + gtid;
+    const unsigned npairs = (unsigned)(np >> 1);
+    const unsigned stride = gridDim.x * blockDim.x;
+    const unsigned gtid = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned iters = (npairs + stride - 1) / stride;    // uniform trip count (warp-collective scatter variants)
+    unsigned q = gtid;
+    for (unsigned it = 0; it < iters; ++it, q += stride) {
         const bool active = q < npairs;
         double2 vv = make_double2(0., 0.), ww = vv, a = vv, b = vv, c = vv;
         if (active) {
-            vv = ld_stream2(v + 2 * q);
-            ww = ld_stream2(w + 2 * q);
-            if (S.k1) a = ld_stream2(S.k1 + 2 * q);
-            if (S.k2) b = ld_stream2(S.k2 + 2 * q);
-            if (S.k3) c = ld_stream2(S.k3 + 2 * q);
+            vv = ld_stream2(v + 2 * (size_t)q);
+            ww = ld_stream2(w + 2 * (size_t)q);
+            if (STAGE >= 2) a = ld_stream2(S.k1 + 2 * (size_t)q);
+            if (STAGE >= 3) b = ld_stream2(S.k2 + 2 * (size_t)q);
+            if (STAGE >= 4) c = ld_stream2(S.k3 + 2 * (size_t)q);
         }
         double2 ks, qn;
         one(vv.x, ww.x, a.x, b.x, c.x, active, ks.x, qn.x);
         one(vv.y, ww.y, a.y, b.y, c.y, active, ks.y, qn.y);
         if (active) {
-            if (S.kout) st_stream2(S.kout + 2 * q, ks);
-            if (S.qout) st_stream2(S.qout + 2 * q, qn);
+            if (STAGE < 4) st_stream2(S.kout + 2 * (size_t)q, ks);
+            if (S.qout) st_stream2(S.qout + 2 * (size_t)q, qn);
         }
     }
     if ((np & 1) && blockIdx.x == 0 && warp == 0) {
         const bool active = (lane == 0);
         const long p = np - 1;
         double ks = 0., qn = 0.;
-        one(active ? v[p] : 0.0, active ? w[p] : 0.0, (active && S.k1) ? S.k1[p] : 0.0, (active && S.k2) ? S.k2[p] : 0.0,
-            (active && S.k3) ? S.k3[p] : 0.0, active, ks, qn);
+        one(active ? v[p] : 0.0, active ? w[p] : 0.0, (active && STAGE >= 2) ? S.k1[p] : 0.0,
+            (active && STAGE >= 3) ? S.k2[p] : 0.0, (active && STAGE >= 4) ? S.k3[p] : 0.0, active, ks, qn);
         if (active) {
-            if (S.kout) S.kout[p] = ks;
+            if (STAGE < 4) S.kout[p] = ks;
             if (S.qout) S.qout[p] = qn;
         }
     }
     flush_grid<VAR>(grid, scratch, out, npar, 0, rep_log2, nwarps, npar);
-    if (VAR != VAR_ATOMIC && F.mode != FINISH_NONE) finish_last_cta(F, out, gridDim.x, npar, grid, scratch);
+    if (F.mode != FINISH_NONE) finish_last_cta(F, out, gridDim.x, npar, grid, scratch);
 }
 
 // Streaming helper: each thread handles U pairs (4 particles for U = 2) per iteration, all loads issued
@@ -275,7 +288,7 @@ __global__ void __launch_bounds__(512, 2)
 k_v_moments(const double* __restrict__ v, long np, VCell m, const double* __restrict__ poly, double* __restrict__ out)
 {
     extern __shared__ double psh[];
-    for (int i = threadIdx.x; i < m.ncell * K; i += blockDim.x) psh[i] = poly[i];
+    load_poly<K>(psh, poly, m.ncell);
     __syncthreads();
     double s[5] = {0., 0., 0., 0., 0.};
     auto acc = [&](double vp) {
@@ -341,7 +354,7 @@ k_v_rhs(const double* __restrict__ v, long np, VCell m, const double* __restrict
         const double* __restrict__ mom, double nu, double* __restrict__ vdot)
 {
     extern __shared__ double psh[];
-    for (int i = threadIdx.x; i < m.ncell * K; i += blockDim.x) psh[i] = poly[i];
+    load_poly<K>(psh, poly, m.ncell);
     __syncthreads();
     const double A1 = mom[5], A2 = mom[6];
     auto rhs = [&](double vp) {
@@ -372,7 +385,7 @@ __global__ void k_v_eval(const double* __restrict__ v, long np, VCell m, const d
                          double* __restrict__ f, double* __restrict__ df)
 {
     extern __shared__ double psh[];
-    for (int i = threadIdx.x; i < m.ncell * K; i += blockDim.x) psh[i] = poly[i];
+    load_poly<K>(psh, poly, m.ncell);
     __syncthreads();
     const long stride = (long)gridDim.x * blockDim.x;
     for (long p = (long)blockIdx.x * blockDim.x + threadIdx.x; p < np; p += stride) {
@@ -562,29 +575,37 @@ void project_dev(vm_vspline* s, const double* v, const double* w, long np)
     after_deposit(s, d);
 }
 
-template <int K, int VAR>
+template <int K, int VAR, int STAGE>
 void launch_stage_inst(vm_vspline* s, const VDepSetup& d, const double* v, const double* w, long np, const StageParams& S)
 {
     vm_ctx* ctx = s->ctx;
     static size_t configured[64] = {};
     size_t& conf = configured[ctx->device & 63];
     if (d.pl.smem > conf) {
-        VM_CUDA(cudaFuncSetAttribute(k_lb_stage<K, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d.pl.smem));
+        VM_CUDA(cudaFuncSetAttribute(k_lb_stage<K, VAR, STAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d.pl.smem));
         conf = d.pl.smem;
     }
-    k_lb_stage<K, VAR><<<d.pl.grid, d.pl.threads, d.pl.smem, ctx->stream>>>(v, w, np, vcell(s), s->cellpoly, s->poly,
-                                                                         s->moments, S, s->npar, d.pl.rep_log2, d.out, d.F);
+    k_lb_stage<K, VAR, STAGE><<<d.pl.grid, d.pl.threads, d.pl.smem, ctx->stream>>>(
+        v, w, np, vcell(s), s->cellpoly, s->poly, s->moments, S, s->npar, d.pl.rep_log2, d.out, d.F);
     VM_LAUNCHED(ctx);
 }
 
-template <int K>
-void launch_stage(vm_vspline* s, const VDepSetup& d, const double* v, const double* w, long np, const StageParams& S)
+// the stage pass exists in the lane-private and the match-grouped flavour (the latter handles any replica count)
+template <int K, int STAGE>
+void launch_stage_var(vm_vspline* s, const VDepSetup& d, const double* v, const double* w, long np, const StageParams& S)
 {
-    switch (d.pl.var) {
-        case VAR_PRIV: launch_stage_inst<K, VAR_PRIV>(s, d, v, w, np, S); break;
-        case VAR_MATCH: launch_stage_inst<K, VAR_MATCH>(s, d, v, w, np, S); break;
-        case VAR_XOR: launch_stage_inst<K, VAR_XOR>(s, d, v, w, np, S); break;
-        default: launch_stage_inst<K, VAR_ATOMIC>(s, d, v, w, np, S); break;
+    if (d.pl.var == VAR_PRIV) launch_stage_inst<K, VAR_PRIV, STAGE>(s, d, v, w, np, S);
+    else launch_stage_inst<K, VAR_MATCH, STAGE>(s, d, v, w, np, S);
+}
+
+template <int K>
+void launch_stage(vm_vspline* s, const VDepSetup& d, const double* v, const double* w, long np, const StageParams& S, int stage)
+{
+    switch (stage) {
+        case 1: launch_stage_var<K, 1>(s, d, v, w, np, S); break;
+        case 2: launch_stage_var<K, 2>(s, d, v, w, np, S); break;
+        case 3: launch_stage_var<K, 3>(s, d, v, w, np, S); break;
+        default: launch_stage_var<K, 4>(s, d, v, w, np, S); break;
     }
 }
 
@@ -595,7 +616,7 @@ void moments_dev(vm_vspline* s, const double* v, long np, int conservative)
         int grid, threads;
         geometry(ctx, &grid, &threads);
         double* out = vm_partials(ctx, (size_t)grid * 8);
-        const size_t smem = (size_t)s->ncell * s->order * sizeof(double);
+        const size_t smem = (size_t)s->ncell * (s->order | 1) * sizeof(double);
         VM_ORDER_SWITCH(s->order, k_v_moments<K><<<grid, threads, smem, ctx->stream>>>(v, np, vcell(s), s->poly, out));
         VM_LAUNCHED(ctx);
         k_reduce_rows8<<<1, 256, 0, ctx->stream>>>(out, grid, s->moments);
@@ -613,7 +634,7 @@ void rhs_dev(vm_vspline* s, const double* v, const double* w, long np, double nu
     moments_dev(s, v, np, conservative);
     int grid, threads;
     geometry(ctx, &grid, &threads);
-    const size_t smem = (size_t)s->ncell * s->order * sizeof(double);
+    const size_t smem = (size_t)s->ncell * (s->order | 1) * sizeof(double);
     VM_ORDER_SWITCH(s->order, k_v_rhs<K><<<grid, threads, smem, ctx->stream>>>(v, np, vcell(s), s->poly, s->moments, nu, vdot));
     VM_LAUNCHED(ctx);
 }
@@ -777,7 +798,7 @@ int vm_vspline_eval(vm_vspline* s, const double* v_host, long n, double* f_host,
             VM_CUDA(cudaMemcpyAsync(buf, v_host, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
             int grid = (int)((n + 255) / 256);
             if (grid > ctx->sm_count * 4) grid = ctx->sm_count * 4;
-            const size_t smem = (size_t)s->ncell * s->order * sizeof(double);
+            const size_t smem = (size_t)s->ncell * (s->order | 1) * sizeof(double);
             VM_ORDER_SWITCH(s->order, k_v_eval<K><<<grid, 256, smem, ctx->stream>>>(buf, n, vcell(s), s->poly, buf + n, buf + 2 * n));
             VM_LAUNCHED(ctx);
             if (f_host) VM_CUDA(cudaMemcpyAsync(f_host, buf + n, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
@@ -876,7 +897,7 @@ int vm_lb_rk438_run(vm_vspline* s, vm_particles* p, double dt, int nsteps, doubl
             // plus the 8 B/particle moments pass for the conservative operator
             project_dev(s, p->v, p->w, np);
             moments_dev(s, p->v, np, conservative);
-            const size_t extra = (size_t)s->ncell * s->order;    // polynomial table lives in shared memory too
+            const size_t extra = (size_t)s->ncell * (s->order | 1);    // polynomial table lives in shared memory too
             auto stage = [&](const double* pk1, const double* pk2, const double* pk3, double a1, double a2, double a3,
                              double c1, double c2, double c3, double cs, double* kout, double* qout) {
                 StageParams S{};
@@ -886,8 +907,10 @@ int vm_lb_rk438_run(vm_vspline* s, vm_particles* p, double dt, int nsteps, doubl
                 S.kout = kout; S.dt = dt; S.nu = nu;
                 S.qout = (conservative || qout == p->v) ? qout : nullptr;   // LB needs no stored stage state
                 VDepSetup d = vdep_setup(s, (int)extra);
+                if (d.pl.var == VAR_ATOMIC) throw vm_error(VM_ERR_UNSUPPORTED, "fused RK438 stage: no atomic deposit variant");
+                const int stage_no = pk3 ? 4 : (pk2 ? 3 : (pk1 ? 2 : 1));
                 vm_prof_mark(ctx);
-                VM_ORDER_SWITCH(s->order, launch_stage<K>(s, d, p->v, p->w, np, S));
+                VM_ORDER_SWITCH(s->order, launch_stage<K>(s, d, p->v, p->w, np, S, stage_no));
                 vm_prof_mark(ctx);
                 after_deposit(s, d);
                 moments_dev(s, qout, np, conservative);
