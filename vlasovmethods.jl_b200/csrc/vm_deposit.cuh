@@ -143,7 +143,7 @@ __device__ __forceinline__ void flush_grid(const double* __restrict__ grid, doub
 // GPU, also solves the periodic Poisson system -- the reduce and solve launches of a step disappear.
 // Used for n <= VM_FUSE_MAX_N; larger grids use the separate multi-CTA kernels.
 #define VM_FUSE_MAX_N 128
-enum { FINISH_NONE = 0, FINISH_REDUCE = 1, FINISH_REDUCE_SOLVE = 2, FINISH_EXCHANGE_SOLVE = 3 };
+enum { FINISH_NONE = 0, FINISH_REDUCE = 1, FINISH_REDUCE_SOLVE = 2, FINISH_EXCHANGE_SOLVE = 3, FINISH_REDUCE_VSOLVE = 4 };
 
 __device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v)
 {
@@ -176,6 +176,12 @@ struct FinishParams {
     double* inbox;                      // this rank's inbox
     double* peer[VM_MAX_PEERS];         // every rank's inbox as mapped on this device (peer[rank] == inbox)
     unsigned* err;
+    // FINISH_REDUCE_VSOLVE (v-space projection): coef = Minv * rhs, then one polynomial per cell
+    const double* minv;                 // nv x nv
+    const double* cellpoly;             // ncell x k x k
+    double* coef;                       // npar (parent indexing)
+    double* poly;                       // ncell x k
+    int nv, off, ncell, k;
 };
 
 __device__ __forceinline__ void finish_last_cta(const FinishParams& F, const double* rows, int nrows, int n,
@@ -270,6 +276,28 @@ __device__ __forceinline__ void finish_last_cta(const FinishParams& F, const dou
         }
         __syncthreads();
         if (t < n) F.dcoef[t] = (phi_sh[t + 1 == n ? 0 : t + 1] - phi_sh[t]) * F.inv_h;
+    }
+    if (F.mode == FINISH_REDUCE_VSOLVE) {
+        // same arithmetic (and bits) as k_v_solve + k_v_poly: one warp per matrix row, fixed xor tree
+        __syncthreads();
+        double* c_sh = sm_a + n;                     // parent-indexed coefficients
+        const int lane = t & 31, wid = t >> 5, nw = T >> 5;
+        if (t < n) c_sh[t] = 0.0;
+        __syncthreads();
+        for (int i = wid; i < F.nv; i += nw) {
+            double s = 0.0;
+            for (int j = lane; j < F.nv; j += 32) s = fma(__ldg(F.minv + (size_t)i * F.nv + j), r_sh[F.off + j], s);
+            s = warp_sum(s);
+            if (lane == 0) c_sh[F.off + i] = s;
+        }
+        __syncthreads();
+        if (t < n) F.coef[t] = c_sh[t];
+        for (int idx = t; idx < F.ncell * F.k; idx += T) {
+            const int c = idx / F.k, mm = idx - c * F.k;
+            double s = 0.0;
+            for (int j = 0; j < F.k; ++j) s = fma(c_sh[c + j], __ldg(F.cellpoly + ((size_t)c * F.k + j) * F.k + mm), s);
+            F.poly[idx] = s;
+        }
     }
     if (t == 0) *F.ticket = 0u;      // ready for the next launch on this stream
 }

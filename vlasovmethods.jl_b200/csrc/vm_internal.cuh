@@ -114,6 +114,7 @@ struct vm_vspline {
     double *moments = nullptr;         // device 8: [5 sums, A1, A2, spare]
     double *diag = nullptr;            // device rows [t, sum v, sum v^2, spare]
     int diag_rows = 0;
+    bool lb_coeffs_set = false;        // moments[5..6] currently hold the LB constants (A1 = 0, A2 = 1)
 };
 
 void vm_set_error(vm_ctx* ctx, const std::string& msg);

@@ -283,9 +283,21 @@ k_lb_stage(const double* v, const double* __restrict__ w, long np, VCell m, cons
 #define VM_STREAM_PAIRS 2
 
 // five unweighted particle sums: [sum f, sum v f, sum v^2 f, sum f', sum v f']
+// mom = [5 sums, A1, A2]; with `ticket` != nullptr the last CTA to finish sums the per-CTA rows in the
+// order of k_reduce_rows8 and evaluates compute_coefficients -- two launches fewer per right-hand side.
+__device__ __forceinline__ void clb_coefficients(double* __restrict__ mom)
+{
+    const double n = mom[0], nu = mom[1], ne = mom[2];
+    const double B1 = -mom[3], B2 = -mom[4];
+    const double den = n * ne - nu * nu;
+    mom[5] = (ne * B1 - nu * B2) / den;
+    mom[6] = -(nu * B1 - n * B2) / den;
+}
+
 template <int K>
 __global__ void __launch_bounds__(512, 2)
-k_v_moments(const double* __restrict__ v, long np, VCell m, const double* __restrict__ poly, double* __restrict__ out)
+k_v_moments(const double* __restrict__ v, long np, VCell m, const double* __restrict__ poly, double* __restrict__ out,
+            unsigned* ticket, double* __restrict__ mom)
 {
     extern __shared__ double psh[];
     load_poly<K>(psh, poly, m.ncell);
@@ -328,6 +340,36 @@ k_v_moments(const double* __restrict__ v, long np, VCell m, const double* __rest
             for (int q = 0; q < nwarps; ++q) t += red[threadIdx.x][q];
         out[(size_t)blockIdx.x * 8 + threadIdx.x] = t;
     }
+    if (ticket) {
+        __shared__ int s_last;
+        __shared__ double fin[32][8];
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1u);
+        __syncthreads();
+        if (!s_last) return;
+        __threadfence();
+        const int nrows = gridDim.x;
+        if (threadIdx.x < 256) {                     // same order as k_reduce_rows8
+            const int c = threadIdx.x & 7, ch = threadIdx.x >> 3;
+            const int len = (nrows + 31) / 32;
+            double t = 0.0;
+            for (int r = ch * len; r < min(nrows, (ch + 1) * len); ++r) t += __ldcg(out + (size_t)r * 8 + c);
+            fin[ch][c] = t;
+        }
+        __syncthreads();
+        if (threadIdx.x < 8) {
+            double t = 0.0;
+            for (int q = 0; q < 32; ++q) t += fin[q][threadIdx.x];
+            if (threadIdx.x < 5) mom[threadIdx.x] = t;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            clb_coefficients(mom);
+            *ticket = 0u;
+        }
+    }
 }
 
 // A1, A2 of compute_coefficients (lenard_bernstein_conservative.jl:13-18) from the five sums
@@ -335,11 +377,7 @@ __global__ void k_clb_coeffs(double* __restrict__ mom, int conservative)
 {
     if (threadIdx.x == 0) {
         if (conservative) {
-            const double n = mom[0], nu = mom[1], ne = mom[2];
-            const double B1 = -mom[3], B2 = -mom[4];
-            const double den = n * ne - nu * nu;
-            mom[5] = (ne * B1 - nu * B2) / den;
-            mom[6] = -(nu * B1 - n * B2) / den;
+            clb_coefficients(mom);
         } else {
             mom[5] = 0.0;   // LB: vdot = -nu (f' + v f)
             mom[6] = 1.0;
@@ -546,6 +584,11 @@ VDepSetup vdep_setup(vm_vspline* s, int extra_doubles)
         d.F.mode = FINISH_REDUCE;           // last CTA sums the per-CTA rows in a fixed order
         d.F.ticket = ctx->ticket;
         d.F.rhs = s->rhs;
+        if (ctx->nranks == 1) {             // single GPU: the mass solve and the polynomial table too
+            d.F.mode = FINISH_REDUCE_VSOLVE;
+            d.F.minv = s->minv; d.F.cellpoly = s->cellpoly; d.F.coef = s->coef; d.F.poly = s->poly;
+            d.F.nv = s->nv; d.F.off = s->bc ? 1 : 0; d.F.ncell = s->ncell; d.F.k = s->order;
+        }
     }
     return d;
 }
@@ -554,6 +597,7 @@ VDepSetup vdep_setup(vm_vspline* s, int extra_doubles)
 void after_deposit(vm_vspline* s, const VDepSetup& d)
 {
     vm_ctx* ctx = s->ctx;
+    if (d.F.mode == FINISH_REDUCE_VSOLVE) return;      // already done by the pass's last CTA
     if (d.F.mode == FINISH_NONE) vm_reduce_rows(ctx, d.out, d.pl.grid, s->npar, s->rhs);
     vm_allreduce_sum(ctx, s->rhs, (size_t)s->npar);
     const int off = s->bc ? 1 : 0;
@@ -613,18 +657,27 @@ void moments_dev(vm_vspline* s, const double* v, long np, int conservative)
 {
     vm_ctx* ctx = s->ctx;
     if (conservative) {
+        s->lb_coeffs_set = false;                     // moments[5..6] are about to hold A1, A2 of the conservative model
         int grid, threads;
         geometry(ctx, &grid, &threads);
+        if (threads < 256) threads = 256;             // the fused finish uses 256 threads
         double* out = vm_partials(ctx, (size_t)grid * 8);
         const size_t smem = (size_t)s->ncell * (s->order | 1) * sizeof(double);
-        VM_ORDER_SWITCH(s->order, k_v_moments<K><<<grid, threads, smem, ctx->stream>>>(v, np, vcell(s), s->poly, out));
+        const bool fuse = ctx->nranks == 1 && !ctx->no_fuse;
+        unsigned* ticket = fuse ? ctx->ticket : nullptr;
+        VM_ORDER_SWITCH(s->order, k_v_moments<K><<<grid, threads, smem, ctx->stream>>>(v, np, vcell(s), s->poly, out, ticket, s->moments));
         VM_LAUNCHED(ctx);
+        if (fuse) return;                             // sums + A1, A2 done by the last CTA
         k_reduce_rows8<<<1, 256, 0, ctx->stream>>>(out, grid, s->moments);
         VM_LAUNCHED(ctx);
         vm_allreduce_sum(ctx, s->moments, 5);
+        k_clb_coeffs<<<1, 32, 0, ctx->stream>>>(s->moments, 1);
+        VM_LAUNCHED(ctx);
+    } else if (!s->lb_coeffs_set) {
+        k_clb_coeffs<<<1, 32, 0, ctx->stream>>>(s->moments, 0);   // LB: A1 = 0, A2 = 1 (set once)
+        VM_LAUNCHED(ctx);
+        s->lb_coeffs_set = true;
     }
-    k_clb_coeffs<<<1, 32, 0, ctx->stream>>>(s->moments, conservative);
-    VM_LAUNCHED(ctx);
 }
 
 void rhs_dev(vm_vspline* s, const double* v, const double* w, long np, double nu, int conservative, double* vdot)
