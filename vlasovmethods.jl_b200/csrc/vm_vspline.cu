@@ -48,10 +48,9 @@ __device__ __forceinline__ void vdeposit_one(double vp, double wp, bool active, 
     active = active && vcell_of(m, vp, c, xi);
     double val[K];
     if (!active) wp = 0.0;
-    if (c >= K - 1 && c <= m.ncell - K) {
-        bspline_uniform_w<K>(xi, wp, val);                // interior cell: uniform cardinal splines (x weight)
-    } else {
-        const double* A = cellpoly + (size_t)c * K * K;   // clamped end: exact polynomial pieces
+    bspline_uniform_w<K>(xi, wp, val);                    // interior cells: uniform cardinal splines (x weight)
+    if (c < K - 1 || c > m.ncell - K) {                   // rare: the 2(K-1) clamped end cells, exact pieces
+        const double* A = cellpoly + (size_t)c * K * K;
 #pragma unroll
         for (int j = 0; j < K; ++j) {
             double s = __ldg(A + j * K + K - 1);
@@ -80,32 +79,40 @@ k_v_deposit(const double* __restrict__ v, const double* __restrict__ w, long np,
     double* wg = (VAR == VAR_ATOMIC) ? grid : grid + warp * gsz;
     const int rep = ((VAR == VAR_ATOMIC) ? warp : lane) & ((1 << rep_log2) - 1);
 
-    constexpr int U = 2;          // pairs in flight per thread (16 B/particle pass: see k_vp_pass)
-    const long npairs = np >> 1;
-    const long stride = (long)gridDim.x * blockDim.x;
-    const long gtid = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long iters = (npairs + U * stride - 1) / (U * stride);
-    double2 cv[U], cw[U], nv[U], nw[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-        cv[u] = cw[u] = nv[u] = nw[u] = make_double2(0., 0.);
-        const long q = u * stride + gtid;
-        if (q < npairs) { cv[u] = ld_stream2(v + 2 * q); cw[u] = ld_stream2(w + 2 * q); }
-    }
-    for (long it = 0; it < iters; ++it) {
-        const long base = it * U * stride + gtid;
+    // 16 B/particle, issue-bound pass: same loop shape as the x-space deposit-only pass (two pairs in
+    // flight per thread, unrolled twice over two register buffer sets, 32-bit pair indices)
+    constexpr int U = 2;
+    const unsigned npairs = (unsigned)(np >> 1);
+    const unsigned stride = gridDim.x * blockDim.x;
+    const unsigned gtid = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned chunk = U * stride;
+    const unsigned iters = (npairs + chunk - 1) / chunk;
+    double2 Av[U], Aw[U], Bv[U], Bw[U];
+    auto load = [&](double2 (&bv)[U], double2 (&bw)[U], unsigned q0) {
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const long qn = base + (U + u) * stride;
-            if (qn < npairs) { nv[u] = ld_stream2(v + 2 * qn); nw[u] = ld_stream2(w + 2 * qn); }
+            const unsigned q = q0 + u * stride;
+            bw[u] = make_double2(0., 0.);
+            if (q < npairs) { bv[u] = ld_stream2(v + 2 * (size_t)q); bw[u] = ld_stream2(w + 2 * (size_t)q); }
         }
+    };
+    auto work = [&](double2 (&bv)[U], double2 (&bw)[U], unsigned q0) {
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const bool active = (base + u * stride) < npairs;
-            vdeposit_one<K, VAR>(cv[u].x, cw[u].x, active, m, cellpoly, wg, npar, rep_log2, rep, lane);
-            vdeposit_one<K, VAR>(cv[u].y, cw[u].y, active, m, cellpoly, wg, npar, rep_log2, rep, lane);
-            cv[u] = nv[u]; cw[u] = nw[u];
+            const bool active = (q0 + u * stride) < npairs;
+            vdeposit_one<K, VAR>(bv[u].x, bw[u].x, active, m, cellpoly, wg, npar, rep_log2, rep, lane);
+            vdeposit_one<K, VAR>(bv[u].y, bw[u].y, active, m, cellpoly, wg, npar, rep_log2, rep, lane);
         }
+    };
+#pragma unroll
+    for (int u = 0; u < U; ++u) Av[u] = Bv[u] = make_double2(0., 0.);
+    unsigned q = gtid;
+    load(Av, Aw, q);
+    for (unsigned it = 0; it < iters; it += 2, q += 2 * chunk) {
+        load(Bv, Bw, q + chunk);
+        work(Av, Aw, q);
+        load(Av, Aw, q + 2 * chunk);
+        work(Bv, Bw, q + chunk);
     }
     if ((np & 1) && blockIdx.x == 0 && warp == 0) {
         const bool active = (lane == 0);
