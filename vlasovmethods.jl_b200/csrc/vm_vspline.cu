@@ -38,7 +38,9 @@ __device__ __forceinline__ bool vcell_of(const VCell& m, double v, int& c, doubl
 }
 
 // ------------------------------------------------------------ v deposit -----
-template <int K, int VAR>
+// STRAIGHT = true: interior values always computed, the rare clamped-end cells override them (best in the
+// stand-alone deposit pass); false: if/else (best inside the register-tight RK stage pass) -- A/B measured.
+template <int K, int VAR, bool STRAIGHT = true>
 __device__ __forceinline__ void vdeposit_one(double vp, double wp, bool active, const VCell& m,
                                              const double* __restrict__ cellpoly, double* __restrict__ wg,
                                              int npar, int rep_log2, int rep, int lane)
@@ -48,8 +50,9 @@ __device__ __forceinline__ void vdeposit_one(double vp, double wp, bool active, 
     active = active && vcell_of(m, vp, c, xi);
     double val[K];
     if (!active) wp = 0.0;
-    bspline_uniform_w<K>(xi, wp, val);                    // interior cells: uniform cardinal splines (x weight)
-    if (c < K - 1 || c > m.ncell - K) {                   // rare: the 2(K-1) clamped end cells, exact pieces
+    const bool interior = (c >= K - 1 && c <= m.ncell - K);
+    if (STRAIGHT || interior) bspline_uniform_w<K>(xi, wp, val);   // interior cells: uniform cardinal splines (x weight)
+    if (!interior) {                                      // rare: the 2(K-1) clamped end cells, exact pieces
         const double* A = cellpoly + (size_t)c * K * K;
 #pragma unroll
         for (int j = 0; j < K; ++j) {
@@ -244,7 +247,7 @@ k_lb_stage(const double* v, const double* __restrict__ w, long np, VCell m, cons
             t = S.cs * ks;
         }
         qn = fma(S.dt, t, vp);
-        vdeposit_one<K, VAR>(qn, wp, active, m, cellpoly, wg, npar, rep_log2, rep, lane);
+        vdeposit_one<K, VAR, false>(qn, wp, active, m, cellpoly, wg, npar, rep_log2, rep, lane);
     };
 
     const unsigned npairs = (unsigned)(np >> 1);
