@@ -1,7 +1,7 @@
 #!/bin/bash
 # A/B of kernel revisions on ONE box: same bench, different builds of the same ABI.
 for L in "$@"; do
-  export VLASOV_B200_LIB=$PWD/ab/lib_$L.so
+  export VLASOV_B200_LIB=$PWD/tools/ab/lib_$L.so
   python bench.py --steps 100 --warmup 3 --no-cpu 2>/dev/null | python -c "
 import sys,json
 d=json.loads(sys.stdin.read().strip().splitlines()[-1])
