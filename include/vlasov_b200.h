@@ -108,6 +108,17 @@ int vm_particles_upload_soa(vm_particles* p, const double* x, const double* v, c
 int vm_particles_download_soa(vm_particles* p, double* x, double* v, double* w);
 int vm_particles_copy(vm_particles* dst, vm_particles* src);
 
+/* Asynchronous, decimated snapshots for the driver loops (run!(::SplittingMethod) writes the full state
+ * after every step, src/methods/splitting.jl:42 -- 1.6 GB per step at 1e8 particles).
+ * vm_particles_snapshot_begin copies x and v (either may be NULL) into a device staging buffer on the
+ * context's stream and starts the device->host copy into the caller's buffers on a second stream; the
+ * call returns at once and stepping may continue.  vm_particles_snapshot_wait blocks until the data has
+ * landed.  Host buffers should be page-locked (vm_host_alloc) for the copy to overlap with compute. */
+int vm_particles_snapshot_begin(vm_particles* p, double* x_host, double* v_host);
+int vm_particles_snapshot_wait(vm_particles* p);
+int vm_host_alloc(size_t bytes, void** out);   /* page-locked host memory */
+int vm_host_free(void* ptr);
+
 /* Device-side synthetic loads reproducing the *distributions* of
  * src/examples/*.jl (the reference draws from Julia's unseeded global RNG, so
  * streams cannot match).  Counter-based Philox4x32-10 keyed by

@@ -246,6 +246,30 @@ def test_mirror_splitting_method(vm, oracle, ctx, rng, tmp_path):
     vm.set_default_context(None)
 
 
+def test_async_snapshot(vm, ctx, rng):
+    """Snapshot taken asynchronously while stepping continues == state at the time of the call."""
+    npart = 300001
+    a, b = 0.0, 2 * math.pi / 0.3
+    x = rng.uniform(a, b, npart); v = rng.standard_normal(npart); w = np.full(npart, (b - a) / npart)
+    fld = vm.DeviceField(ctx, a, b, 4, 16, 0)
+    p = vm.DeviceParticles(ctx, npart)
+    p.upload(x, v, w)
+    fld.run(p, 0.1, 3, 0, 0, 1.0)
+    x3, v3, _ = p.download(w=False)
+    bx, bv = vm.PinnedArray(npart), vm.PinnedArray(npart)
+    p.snapshot_begin(bx.array, bv.array)
+    fld.run(p, 0.1, 4, 0, 0, 1.0)          # keeps the GPU busy while the copy drains
+    p.snapshot_wait()
+    assert np.array_equal(bx.array, x3) and np.array_equal(bv.array, v3)
+    x7 = p.download(w=False)[0]
+    assert not np.array_equal(x7, x3)
+    p.snapshot_begin(None, bv.array)       # v only, twice in a row (staging buffer reuse)
+    p.snapshot_begin(bx.array, None)
+    p.snapshot_wait()
+    assert np.array_equal(bx.array, x7)
+    vm.DeviceParticles(ctx, 0).snapshot_begin(None, None)
+
+
 def test_particles_aos_roundtrip_and_kick_drift(vm, oracle, ctx, rng):
     npart = 12347
     z = rng.standard_normal((npart, 3))
@@ -368,7 +392,7 @@ def test_vp_run_bitwise_reproducible(vm, ctx, rng):
     assert outs[0] == outs[1] == outs[2]
 
 
-def test_mirror_lenard_bernstein(vm, oracle, ctx, rng):
+def test_mirror_lenard_bernstein(vm, oracle, ctx, rng, tmp_path):
     vm.set_default_context(ctx)
     npart = 1000
     dist = vm.initialize_(vm.ParticleDistribution(1, 1, npart), vm.DoubleMaxwellian((-10.0, 10.0), 2.0), seed=11)
@@ -377,7 +401,10 @@ def test_mirror_lenard_bernstein(vm, oracle, ctx, rng):
     sdist = vm.SplineDistribution(1, 1, 41, 4, (-10.0, 10.0), "Dirichlet")
     model = vm.ConservativeLenardBernstein(dist, vm.CollisionEntropy(sdist))
     integ = vm.GeometricIntegrator(model, (0.0, 0.05), 1e-2)
-    vm.run_(integ, None, diag_every=1)
+    vm.run_(integ, str(tmp_path / "lb.npz"), diag_every=1, save_every=2)
+    zz = np.load(tmp_path / "lb.npz")
+    assert zz["z"].shape == (npart, 4) and np.array_equal(zz["z"][:, 0], v0) and np.allclose(zz["t"], [0, 0.02, 0.04, 0.05])
+    assert np.array_equal(zz["z"][:, -1], dist.particles.v[0])
     M = oracle.dirichlet_mass(-10.0, 10.0, 41, 4)
     vo = v0.copy()
     for _ in range(5):

@@ -7,7 +7,8 @@ binding), core.py (handle wrappers), api.py (mirror of the reference's new API),
 (mirror of src/electric_field.jl + src/vlasov_poisson.jl), sharding.py (one process per GPU)."""
 from . import _lib
 from ._lib import VMError, build, lib
-from .core import Context, DeviceField, DeviceParticles, DeviceVSpline, default_context, set_default_context
+from .core import (Context, DeviceField, DeviceParticles, DeviceVSpline, PinnedArray, default_context,
+                   set_default_context)
 from .api import *          # noqa: F401,F403
 from .api import (initialize_, projection_, projection, update_ as update_potential_solver_, run_, LB_rhs_, CLB_rhs_,
                   update_potential_, compute_coefficients, compute_f_densities, compute_df_densities)

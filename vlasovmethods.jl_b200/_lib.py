@@ -47,6 +47,10 @@ SIGNATURES = {
     "vm_particles_upload_soa": (_i, [_vp, _dp, _dp, _dp]),
     "vm_particles_download_soa": (_i, [_vp, _dp, _dp, _dp]),
     "vm_particles_copy": (_i, [_vp, _vp]),
+    "vm_particles_snapshot_begin": (_i, [_vp, _dp, _dp]),
+    "vm_particles_snapshot_wait": (_i, [_vp]),
+    "vm_host_alloc": (_i, [C.c_size_t, C.POINTER(_vp)]),
+    "vm_host_free": (_i, [_vp]),
     "vm_particles_fill": (_i, [_vp, _i, _dp, _i, C.c_ulonglong, _l, _l]),
     "vm_field_create": (_i, [_vp, _d, _d, _i, _i, _i, C.POINTER(_vp)]),
     "vm_field_destroy": (_i, [_vp]),

@@ -409,6 +409,36 @@ def _chunks(nt, save_every):
     return out
 
 
+class _SnapshotWriter:
+    """Decimated, asynchronous snapshots: the device->host copy of snapshot i (pinned double buffers, second
+    stream) overlaps with the steps of chunk i+1; replaces the per-step HDF5 write of splitting.jl:42."""
+
+    def __init__(self, dev: DeviceParticles, nsnaps: int, with_x: bool):
+        from .core import PinnedArray
+        self.dev, self.with_x = dev, with_x
+        self.bufs = [(PinnedArray(dev.n) if with_x else None, PinnedArray(dev.n)) for _ in range(2)]
+        self.z = np.empty((2, dev.n, nsnaps)) if with_x else np.empty((dev.n, nsnaps))
+        self.i = 0            # snapshots started
+        self.done = 0         # snapshots stored
+
+    def begin(self):
+        bx, bv = self.bufs[self.i % 2]
+        self.dev.snapshot_begin(bx.array if bx is not None else None, bv.array)
+        self.i += 1
+
+    def finish(self):
+        if self.done == self.i:
+            return
+        self.dev.snapshot_wait()
+        bx, bv = self.bufs[self.done % 2]
+        if self.with_x:
+            self.z[0, :, self.done] = bx.array
+            self.z[1, :, self.done] = bv.array
+        else:
+            self.z[:, self.done] = bv.array
+        self.done += 1
+
+
 def _run_splitting(method: SplittingMethod, nt, h5file, save_every, diag_every):
     model = method.model
     dist, pot = model.distribution, model.potential
@@ -417,22 +447,28 @@ def _run_splitting(method: SplittingMethod, nt, h5file, save_every, diag_every):
     if method.field_source == "model_ics":
         update_potential_(model)          # phi of the model's (initial) particles, never refreshed
         flags |= L.VM_RUN_FROZEN_FIELD
-    snaps, times, diags = [], [], []
+    chunks = _chunks(nt, save_every)
     keep = h5file is not None or save_every > 0
+    snaps = _SnapshotWriter(dev, len(chunks) + 1, True) if keep else None
+    times, diags = [method.tspan[0]], []
     if keep:
-        snaps.append(np.stack(dev.download(w=False)[:2])); times.append(method.tspan[0])
+        snaps.begin()
     done = 0
-    for n in _chunks(nt, save_every):
+    for n in chunks:
         de = diag_every if (diag_every > 0 and n % diag_every == 0) else 0
-        d = pot.field.run(dev, method.tstep, n, de, flags, 1.0)
+        d = pot.field.run(dev, method.tstep, n, de, flags, 1.0)     # enqueued; overlaps the pending snapshot copy
         if d is not None:
             diags.append(d if not diags else d[1:])
         done += n
+        times.append(method.tspan[0] + done * method.tstep)
         if keep:
-            snaps.append(np.stack(dev.download(w=False)[:2])); times.append(method.tspan[0] + done * method.tstep)
+            snaps.finish()
+            snaps.begin()
+    if keep:
+        snaps.finish()
     method.diagnostics = np.concatenate(diags) if diags else None
     if h5file is not None:
-        np.savez(h5file, z=np.stack(snaps, axis=-1), t=np.asarray(times))
+        np.savez(h5file, z=snaps.z, t=np.asarray(times))
     if dist.particles.data is not None:
         dist.to_host()                    # copy!(model.distribution.particles.z, solstep.q)
     return dist
@@ -442,23 +478,29 @@ def _run_rk438(method: GeometricIntegrator, nt, h5file, save_every, diag_every):
     model = method.model
     dev = model.dist.device()
     vs = model.ent.dist.vs
-    snaps, times, diags = [], [], []
+    chunks = _chunks(nt, save_every)
     keep = h5file is not None or save_every > 0
+    snaps = _SnapshotWriter(dev, len(chunks) + 1, False) if keep else None
+    times, diags = [method.tspan[0]], []
     if keep:
-        snaps.append(dev.download(x=False, w=False)[1]); times.append(method.tspan[0])
+        snaps.begin()
     done = 0
-    for n in _chunks(nt, save_every):
+    for n in chunks:
         de = diag_every if (diag_every > 0 and n % diag_every == 0) else 0
         d = vs.rk438_run(dev, method.tstep, n, model.ν, model.conservative, de)
         if d is not None:
             d = d.copy(); d[:, 0] += method.tspan[0] + done * method.tstep
             diags.append(d if not diags else d[1:])
         done += n
+        times.append(method.tspan[0] + done * method.tstep)
         if keep:
-            snaps.append(dev.download(x=False, w=False)[1]); times.append(method.tspan[0] + done * method.tstep)
+            snaps.finish()
+            snaps.begin()
+    if keep:
+        snaps.finish()
     method.diagnostics = np.concatenate(diags) if diags else None
     if h5file is not None:
-        np.savez(h5file, z=np.stack(snaps, axis=-1), t=np.asarray(times))
+        np.savez(h5file, z=snaps.z, t=np.asarray(times))
     if model.dist.particles.data is not None:
         model.dist.to_host()              # model.dist.particles.v[1,:] .= solstep.q
     return model.dist

@@ -113,6 +113,25 @@ def set_default_context(ctx: Context | None):
     _default_ctx = ctx
 
 
+class PinnedArray:
+    """float64 numpy view of page-locked host memory from vm_host_alloc (freed with the object)."""
+
+    def __init__(self, n: int):
+        self._ptr = C.c_void_p()
+        L.check(L.lib().vm_host_alloc(C.c_size_t(8 * max(int(n), 1)), C.byref(self._ptr)))
+        buf = (C.c_double * int(n)).from_address(self._ptr.value)
+        self.array = np.frombuffer(buf, dtype=np.float64, count=int(n))
+
+    def __del__(self):
+        try:
+            if getattr(self, "_ptr", None) is not None and self._ptr.value:
+                self.array = None
+                L.lib().vm_host_free(self._ptr)
+                self._ptr = C.c_void_p()
+        except Exception:
+            pass
+
+
 class DeviceParticles:
     """vm_particles: device SoA x[N], v[N], w[N]."""
 
@@ -156,6 +175,15 @@ class DeviceParticles:
         arrs = list(out) if out is not None else [np.empty(self.n) if f else None for f in (x, v, w)]
         L.check(L.lib().vm_particles_download_soa(self._h, *[L.dptr(a) for a in arrs]), self.ctx._h)
         return tuple(arrs)
+
+    def snapshot_begin(self, x_host=None, v_host=None):
+        """Start an asynchronous copy of x and/or v into (ideally pinned) host arrays; returns at once."""
+        for a in (x_host, v_host):
+            assert a is None or (a.dtype == np.float64 and a.flags.c_contiguous and a.size == self.n)
+        L.check(L.lib().vm_particles_snapshot_begin(self._h, L.dptr(x_host), L.dptr(v_host)), self.ctx._h)
+
+    def snapshot_wait(self):
+        L.check(L.lib().vm_particles_snapshot_wait(self._h), self.ctx._h)
 
     def copy_from(self, other: "DeviceParticles"):
         L.check(L.lib().vm_particles_copy(self._h, other._h), self.ctx._h)

@@ -165,6 +165,9 @@ int vm_ctx_create(int device, vm_ctx** out)
         c->smem_optin = prop.sharedMemPerBlockOptin;
         VM_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         for (int i = 0; i < VM_MAX_EVENTS; ++i) VM_CUDA(cudaEventCreate(&c->events[i]));
+        VM_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        VM_CUDA(cudaEventCreateWithFlags(&c->snap_ready, cudaEventDisableTiming));
+        VM_CUDA(cudaEventCreateWithFlags(&c->snap_done, cudaEventDisableTiming));
         VM_CUDA(cudaMalloc(&c->ticket, sizeof(unsigned)));
         VM_CUDA(cudaMemset(c->ticket, 0, sizeof(unsigned)));
         *out = c;
@@ -189,6 +192,9 @@ int vm_ctx_destroy(vm_ctx* ctx)
     }
     for (int i = 0; i < VM_MAX_EVENTS; ++i) if (ctx->events[i]) cudaEventDestroy(ctx->events[i]);
     for (cudaEvent_t e : ctx->prof_events) cudaEventDestroy(e);
+    if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
+    if (ctx->snap_ready) cudaEventDestroy(ctx->snap_ready);
+    if (ctx->snap_done) cudaEventDestroy(ctx->snap_done);
     if (ctx->partials) cudaFree(ctx->partials);
     if (ctx->ticket) cudaFree(ctx->ticket);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
@@ -449,6 +455,7 @@ int vm_particles_destroy(vm_particles* p)
     cudaStreamSynchronize(p->ctx->stream);
     cudaFree(p->x); cudaFree(p->v); cudaFree(p->w);
     if (p->a) cudaFree(p->a);
+    if (p->snap) { cudaStreamSynchronize(p->ctx->copy_stream); cudaFree(p->snap); }
     for (double* q : p->work) if (q) cudaFree(q);
     delete p;
     return VM_OK;
@@ -524,6 +531,61 @@ int vm_particles_download_aos(vm_particles* p, double* z)
     }
     VM_CUDA(cudaStreamSynchronize(p->ctx->stream));
     VM_API_END
+}
+
+int vm_particles_snapshot_begin(vm_particles* p, double* x_host, double* v_host)
+{
+    VM_API_BEGIN(p ? p->ctx : nullptr)
+    VM_REQUIRE(p != nullptr, "vm_particles_snapshot_begin: NULL handle");
+    vm_ctx* ctx = p->ctx;
+    if (p->n > 0 && (x_host || v_host)) {
+        const size_t bytes = (size_t)p->n * sizeof(double);
+        if (!p->snap) VM_CUDA(cudaMalloc(&p->snap, 2 * bytes));
+        // the staging buffer may still be draining to the host from the previous snapshot
+        if (p->snap_pending) VM_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->snap_done, 0));
+        if (x_host) VM_CUDA(cudaMemcpyAsync(p->snap, p->x, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+        if (v_host) VM_CUDA(cudaMemcpyAsync(p->snap + p->n, p->v, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+        VM_CUDA(cudaEventRecord(ctx->snap_ready, ctx->stream));
+        VM_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->snap_ready, 0));
+        if (x_host) VM_CUDA(cudaMemcpyAsync(x_host, p->snap, bytes, cudaMemcpyDeviceToHost, ctx->copy_stream));
+        if (v_host) VM_CUDA(cudaMemcpyAsync(v_host, p->snap + p->n, bytes, cudaMemcpyDeviceToHost, ctx->copy_stream));
+        VM_CUDA(cudaEventRecord(ctx->snap_done, ctx->copy_stream));
+        p->snap_pending = true;
+    }
+    VM_API_END
+}
+
+int vm_particles_snapshot_wait(vm_particles* p)
+{
+    VM_API_BEGIN(p ? p->ctx : nullptr)
+    VM_REQUIRE(p != nullptr, "vm_particles_snapshot_wait: NULL handle");
+    if (p->snap_pending) {
+        VM_CUDA(cudaEventSynchronize(p->ctx->snap_done));
+        p->snap_pending = false;
+        vm_check_peer_error(p->ctx);
+    }
+    VM_API_END
+}
+
+int vm_host_alloc(size_t bytes, void** out)
+{
+    vm_ctx* ctx__ = nullptr;
+    try {
+        VM_REQUIRE(out != nullptr, "vm_host_alloc: out is NULL");
+        *out = nullptr;
+        if (cudaMallocHost(out, bytes ? bytes : 1) != cudaSuccess) {
+            (void)cudaGetLastError();
+            throw vm_error(VM_ERR_NOMEM, "vm_host_alloc: cudaMallocHost failed");
+        }
+    }
+    catch (const vm_error& e) { vm_set_error(ctx__, e.what()); return e.code; }
+    return VM_OK;
+}
+
+int vm_host_free(void* ptr)
+{
+    if (ptr) cudaFreeHost(ptr);
+    return VM_OK;
 }
 
 int vm_particles_copy(vm_particles* dst, vm_particles* src)

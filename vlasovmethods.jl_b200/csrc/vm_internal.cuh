@@ -46,6 +46,8 @@ struct vm_ctx {
     std::string last_error;
     unsigned long long launches = 0;
     cudaEvent_t events[VM_MAX_EVENTS] = {};
+    cudaStream_t copy_stream = nullptr;      // device->host snapshot copies overlap with compute
+    cudaEvent_t snap_ready = nullptr, snap_done = nullptr;
     // tuning (0 = auto)
     int ctas_per_sm = 0, threads_per_cta = 0, replicas = 0, profile = 0, no_fuse = 0, no_pdl = 0, force_match = 0;
     // per-launch event brackets of the dominant kernel (profile == 1)
@@ -75,6 +77,8 @@ struct vm_particles {
     double *x = nullptr, *v = nullptr, *w = nullptr;
     double* a = nullptr;        // lazily allocated per-particle work array (E / vdot)
     double* work[5] = {};       // lazily allocated RK stage arrays
+    double* snap = nullptr;     // lazily allocated staging copy of x and v for asynchronous snapshots
+    bool snap_pending = false;
 };
 
 // Map a position to (first basis index, xi) on a uniform periodic grid.
