@@ -302,6 +302,31 @@ def run_gpu(args):
                    "(vm_particles_upload_soa / vm_vp_run / vm_particles_download_soa)",
            "energy_drift": float(abs((diag[-1, 0] + diag[-1, 1]) - (diag[0, 0] + diag[0, 1])) / (diag[0, 0] + diag[0, 1]))}
 
+    # ---------------- secondary numbers (BASELINE metric: "+ deposit HBM GB/s vs peak"; configs[2], [3]) ----------
+    def timed(fn, reps):
+        fn(); ctx.sync(); ctx.event_record(8)
+        for _ in range(reps):
+            fn()
+        ctx.event_record(9)
+        return max_over_ranks(ctx.event_elapsed_ms(8, 9)) / reps
+
+    dep_ms = timed(lambda: fld.deposit(p, 0), 10)            # projection!(potential, dist) alone: 16 B/particle
+    deposit = {"kernel": "k_vp_pass<4,PRIV,DEPOSIT>", "ms": dep_ms, "GBps": 16 * nloc / dep_ms / 1e6,
+               "frac": 16 * nloc / dep_ms / 1e6 / peak, "algorithmic_bytes_per_particle": 16,
+               "shared_atomics": 0, "mode": "deterministic (lane-private replicas)"}
+    secondary = None
+    if not args.no_secondary:
+        vs = vm.DeviceVSpline(ctx, -10.0, 10.0, 41, 4, 1)
+        p.fill(vm._lib.VM_FILL_DOUBLE_MAXWELLIAN, [-10.0, 10.0, 2.0], SEED, lo, ntot)
+        lb = timed(lambda: vs.lb_rhs(p, 1.0, False, to_host=False), 5)
+        clb = timed(lambda: vs.lb_rhs(p, 1.0, True, to_host=False), 5)
+        rk = timed(lambda: vs.rk438_run(p, 1e-3, 5, 1.0, True, 0), 2) / 5
+        secondary = {"particles_total": ntot, "vspline": "41 knots, order 4, Dirichlet, v in (-10,10)",
+                     "lb_rhs_evals_per_s": ntot / lb * 1e3, "lb_rhs_hbm_frac": 32 * nloc / lb / 1e6 / peak,
+                     "clb_rhs_evals_per_s": ntot / clb * 1e3, "clb_rhs_hbm_frac": 40 * nloc / clb / 1e6 / peak,
+                     "clb_rk438_particle_steps_per_s": ntot / rk * 1e3, "clb_rk438_hbm_frac": 200 * nloc / rk / 1e6 / peak}
+        vs.close()
+
     cpu = None
     if world == 1 and rank == 0 and not args.no_cpu:
         try:
@@ -319,7 +344,8 @@ def run_gpu(args):
             "metric": "particle-steps/sec", "value": value, "unit": "particle-steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "roofline": roofline, "deposit": deposit, "secondary": secondary, "cpu_baseline": cpu, "e2e": e2e,
+            "gpu_launches": int(launches), "clocks": clocks,
             "step_hbm_frac": ALG_BYTES_PER_PARTICLE * nloc * args.steps / (ms * 1e-3) / 1e9 / peak,
         }))
     if world > 1:
@@ -346,6 +372,7 @@ def main():
     ap.add_argument("--particles", type=int, default=N_TOTAL)
     ap.add_argument("--atomic", action="store_true", help="use the shared-atomic deposit variant (A/B)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the Lenard-Bernstein secondary numbers")
     ap.add_argument("--no-peer", action="store_true", help="NCCL all-reduce instead of the fused NVLink peer-memory exchange (A/B)")
     ap.add_argument("--no-pdl", action="store_true", help="disable programmatic dependent launch of the pass kernels (A/B)")
     ap.add_argument("--no-fuse", action="store_true", help="separate reduce/solve kernels instead of the last-CTA finish (A/B)")

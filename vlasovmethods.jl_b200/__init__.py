@@ -11,7 +11,8 @@ from .core import (Context, DeviceField, DeviceParticles, DeviceVSpline, PinnedA
                    set_default_context)
 from .api import *          # noqa: F401,F403
 from .api import (initialize_, projection_, projection, update_ as update_potential_solver_, run_, LB_rhs_, CLB_rhs_,
-                  update_potential_, compute_coefficients, compute_f_densities, compute_df_densities)
+                  update_potential_, compute_coefficients, compute_f_densities, compute_df_densities,
+                  s_advection_, s_acceleration_, lorentz_force_, v_advection_, v_acceleration_)
 from . import legacy
 from .legacy import (PoissonSolverPBSplines, PoissonField, ExternalField, ScaledField, ScaledPoissonField,
                      ScaledExternalField, VPIntegratorParameters, VPIntegratorCache, integrate_vp_, energy,

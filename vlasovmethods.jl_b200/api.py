@@ -327,6 +327,40 @@ def update_potential_(model: VlasovPoisson):   # :12-15
     update_(model.potential)
 
 
+# Splitting flows and vector fields of src/models/vlasov_poisson.jl:23-67, acting on the model's device state.
+# (z, zbar are implicit: the particle state lives on the device; dt = t - tbar.)
+def s_advection_(model: VlasovPoisson, dt: float):
+    """s_advection! (:53-58): x <- x + dt * v."""
+    model.distribution.device().drift(dt)
+
+
+def s_acceleration_(model: VlasovPoisson, dt: float):
+    """s_acceleration! (:61-67): update_potential! then v <- v - dt * phi'(x)."""
+    update_potential_(model)
+    model.potential.field.kick(model.distribution.device(), dt, -1.0)
+
+
+def lorentz_force_(model: VlasovPoisson):
+    """lorentz_force! (:23-29): (xdot, vdot) = (v, -phi'(x)) with the potential refreshed from the state.
+    Returns host arrays (xdot, vdot) for generic (unsplit) Runge-Kutta drivers."""
+    update_potential_(model)
+    dev = model.distribution.device()
+    vdot = model.potential.field.gather_E(dev, 1.0)
+    return dev.download(x=False, w=False)[1], vdot
+
+
+def v_advection_(model: VlasovPoisson):
+    """v_advection! (:36-41): (xdot, vdot) = (v, 0)."""
+    v = model.distribution.device().download(x=False, w=False)[1]
+    return v, np.zeros_like(v)
+
+
+def v_acceleration_(model: VlasovPoisson):
+    """v_acceleration! (:44-50): (xdot, vdot) = (0, -phi'(x))."""
+    xdot, vdot = lorentz_force_(model)
+    return np.zeros_like(xdot), vdot
+
+
 class LenardBernstein:                    # src/models/lenard_bernstein.jl:1-9
     conservative = False
 
