@@ -129,10 +129,18 @@ def sample_particles(n, seed=SEED):
     return x, v, w
 
 
+def host_threads():
+    """All host cores this process may use (torchrun exports OMP_NUM_THREADS=1, which must not cap the CPU arm)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_baseline(target_seconds=12.0):
     """C restatement of the reference algorithm on the host cores, bounded sample of the same workload."""
     orc, nlib = native_oracle()
-    threads = orc.max_threads(nlib)
+    threads = host_threads()
     n_s = 4_000_000
     x, v, w = sample_particles(n_s)
     t0 = time.perf_counter()
@@ -158,7 +166,7 @@ def run_reference(args):
     if rank != 0:
         return
     orc, nlib = native_oracle()
-    threads = orc.max_threads(nlib)
+    threads = host_threads()
     n_s = 4_000_000                              # bounded sample of the 1e8-particle workload per step
     x, v, w = sample_particles(n_s)
     for _ in range(args.warmup):
