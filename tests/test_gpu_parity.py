@@ -246,6 +246,40 @@ def test_mirror_splitting_method(vm, oracle, ctx, rng, tmp_path):
     vm.set_default_context(None)
 
 
+def test_uniform_weight_fast_path_is_bitwise_identical(vm, rng):
+    """When every particle carries the same weight the library passes w0 as a kernel parameter instead of
+    streaming w: same arithmetic, so deposits, trajectories and LB right-hand sides must agree bit for bit
+    with the general path (tuning no_uniform_w = 1)."""
+    a, b, n, k = 0.0, 2 * math.pi / 0.3, 16, 4
+    npart = 150001
+    x = rng.uniform(a, b, npart); v = rng.standard_normal(npart); w = np.full(npart, (b - a) / npart)
+    res = []
+    for general in (0, 1):
+        c = vm.Context(0)
+        c.set_tuning("no_uniform_w", general)
+        fld = vm.DeviceField(c, a, b, k, n, 0)
+        p = vm.DeviceParticles(c, npart)
+        p.upload(x, v, w)
+        fld.deposit(p, 0)
+        rhs = fld.rhs.tobytes()
+        d = fld.run(p, 0.1, 6, 3, 0, 1.0)
+        xs, vs_, ws = p.download()
+        vsp = vm.DeviceVSpline(c, -10.0, 10.0, 41, 4, 1)
+        p.upload(v=v, w=np.full(npart, 1.0 / npart))
+        vdot = vsp.lb_rhs(p, 1.0, True)
+        vsp.rk438_run(p, 1e-2, 2, 1.0, True, 0)
+        vend = p.download(x=False, w=False)[1]
+        res.append((rhs, d.tobytes(), xs.tobytes(), vs_.tobytes(), vdot.tobytes(), vend.tobytes()))
+        assert np.array_equal(ws, w)
+        # non-uniform weights after a uniform phase must be picked up again
+        w2 = w.copy(); w2[npart // 2] *= 2.0
+        p.upload(x, v, w2)
+        fld.deposit(p, 0)
+        assert abs(fld.rhs.sum() - w2.sum()) <= 1e-13 * w2.sum()
+        vsp.close(); p.close(); fld.close(); c.close()
+    assert res[0] == res[1]
+
+
 def test_async_snapshot(vm, ctx, rng):
     """Snapshot taken asynchronously while stepping continues == state at the time of the call."""
     npart = 300001

@@ -243,6 +243,7 @@ int vm_ctx_set_tuning(vm_ctx* ctx, const char* key, int value)
     }
     else if (k == "profile") ctx->profile = value;
     else if (k == "force_match") ctx->force_match = value;   // 1: MATCH.ANY grouping instead of xor rounds (A/B)
+    else if (k == "no_uniform_w") ctx->no_uniform_w = value;   // 1: always stream per-particle weights (A/B)
     else if (k == "no_pdl") ctx->no_pdl = value;     // 1: plain stream serialization for the pass kernels (A/B)
     else if (k == "no_fuse") ctx->no_fuse = value;   // 1: separate reduce/solve kernels even for small grids (A/B)
     else throw vm_error(VM_ERR_INVALID, "unknown tuning key: " + k);
@@ -406,6 +407,17 @@ __global__ void __launch_bounds__(256) k_soa_to_aos(const double* __restrict__ x
     }
 }
 
+// flag[0] stays 1 iff every weight has the same bits as w[0]
+__global__ void __launch_bounds__(256) k_weights_uniform(const double* __restrict__ w, long n, int* __restrict__ flag)
+{
+    const long long first = __double_as_longlong(w[0]);
+    bool same = true;
+    const long stride = (long)gridDim.x * blockDim.x;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        same = same && (__double_as_longlong(w[i]) == first);
+    if (!__all_sync(VM_FULL_MASK, same) && (threadIdx.x & 31) == 0) atomicExch(flag, 0);
+}
+
 // Host <-> device transfers of big arrays go through a pair of pinned bounce buffers so that
 // pageable host memory (a Julia Array) still streams at PCIe rate and overlaps with the copy engine.
 void copy_h2d(vm_ctx* ctx, double* dst, const double* src, size_t n)
@@ -418,6 +430,31 @@ void copy_d2h(vm_ctx* ctx, double* dst, const double* src, size_t n)
 }
 
 }  // namespace
+
+bool vm_particles_uniform_weight(vm_particles* p, double* w0)
+{
+    vm_ctx* ctx = p->ctx;
+    if (ctx->no_uniform_w || p->n == 0) return false;
+    if (p->w_dirty) {
+        int* flag = nullptr;
+        VM_CUDA(cudaMalloc(&flag, sizeof(int)));
+        const int one = 1;
+        VM_CUDA(cudaMemcpyAsync(flag, &one, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        k_weights_uniform<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(p->w, p->n, flag);
+        ++ctx->launches;
+        int h = 0;
+        double first = 0.0;
+        VM_CUDA(cudaMemcpyAsync(&h, flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        VM_CUDA(cudaMemcpyAsync(&first, p->w, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        VM_CUDA(cudaStreamSynchronize(ctx->stream));
+        VM_CUDA(cudaFree(flag));
+        p->uniform_w = (h == 1);
+        p->w0 = first;
+        p->w_dirty = false;
+    }
+    if (w0) *w0 = p->w0;
+    return p->uniform_w;
+}
 
 extern "C" {
 
@@ -470,7 +507,7 @@ int vm_particles_upload_soa(vm_particles* p, const double* x, const double* v, c
     if (p->n > 0) {
         if (x) copy_h2d(p->ctx, p->x, x, (size_t)p->n);
         if (v) copy_h2d(p->ctx, p->v, v, (size_t)p->n);
-        if (w) copy_h2d(p->ctx, p->w, w, (size_t)p->n);
+        if (w) { copy_h2d(p->ctx, p->w, w, (size_t)p->n); p->w_dirty = true; }
         VM_CUDA(cudaStreamSynchronize(p->ctx->stream));   // host buffers are only borrowed for the call
     }
     VM_API_END
@@ -496,6 +533,7 @@ int vm_particles_upload_aos(vm_particles* p, const double* z)
     VM_REQUIRE(p != nullptr && z != nullptr, "vm_particles_upload_aos: NULL argument");
     if (p->n > 0) {
         vm_ctx* ctx = p->ctx;
+        p->w_dirty = true;
         // stage in chunks through the scratch buffer to bound the extra device memory
         const long chunk = 1L << 22;   // particles per chunk (96 MiB of AoS)
         double* stage = vm_partials(ctx, (size_t)3 * (size_t)(p->n < chunk ? p->n : chunk));
@@ -599,6 +637,7 @@ int vm_particles_copy(vm_particles* dst, vm_particles* src)
         VM_CUDA(cudaMemcpyAsync(dst->v, src->v, bytes, cudaMemcpyDeviceToDevice, dst->ctx->stream));
         VM_CUDA(cudaMemcpyAsync(dst->w, src->w, bytes, cudaMemcpyDeviceToDevice, dst->ctx->stream));
     }
+    dst->w_dirty = true;
     VM_API_END
 }
 

@@ -49,7 +49,7 @@ struct vm_ctx {
     cudaStream_t copy_stream = nullptr;      // device->host snapshot copies overlap with compute
     cudaEvent_t snap_ready = nullptr, snap_done = nullptr;
     // tuning (0 = auto)
-    int ctas_per_sm = 0, threads_per_cta = 0, replicas = 0, profile = 0, no_fuse = 0, no_pdl = 0, force_match = 0;
+    int ctas_per_sm = 0, threads_per_cta = 0, replicas = 0, profile = 0, no_fuse = 0, no_pdl = 0, force_match = 0, no_uniform_w = 0;
     // per-launch event brackets of the dominant kernel (profile == 1)
     std::vector<cudaEvent_t> prof_events;   // pairs: [2i] start, [2i+1] stop
     size_t prof_used = 0;                    // events in use since the last read
@@ -79,6 +79,11 @@ struct vm_particles {
     double* work[5] = {};       // lazily allocated RK stage arrays
     double* snap = nullptr;     // lazily allocated staging copy of x and v for asynchronous snapshots
     bool snap_pending = false;
+    // weight class: every sampler of the reference produces ONE weight for all particles (w = 1/N or L/N);
+    // then the passes take w0 from the parameter block instead of streaming 8 B/particle from HBM
+    bool w_dirty = true;        // w changed since the last classification
+    bool uniform_w = false;
+    double w0 = 0.0;
 };
 
 // Map a position to (first basis index, xi) on a uniform periodic grid.
@@ -118,6 +123,8 @@ struct vm_vspline {
     double *moments = nullptr;         // device 8: [5 sums, A1, A2, spare]
     double *diag = nullptr;            // device rows [t, sum v, sum v^2, spare]
     int diag_rows = 0;
+    int uw = 0;                        // weight class of the particles of the current call (see vm_particles)
+    double w0 = 0.0;
     bool lb_coeffs_set = false;        // moments[5..6] currently hold the LB constants (A1 = 0, A2 = 1)
 };
 
@@ -128,7 +135,8 @@ double* vm_pinned(vm_ctx* ctx, size_t elems);     // grow-only pinned host scrat
 void vm_allreduce_sum(vm_ctx* ctx, double* dev, size_t count);  // no-op when nranks == 1
 void vm_launch_geometry(vm_ctx* ctx, int* grid, int* threads);
 void vm_prof_mark(vm_ctx* ctx);
-void vm_check_peer_error(vm_ctx* ctx);   // after a stream sync: throws if a peer exchange timed out   // records the next event of a start/stop pair when profiling is on
+void vm_check_peer_error(vm_ctx* ctx);
+bool vm_particles_uniform_weight(vm_particles* p, double* w0);   // classifies w on first use after a change   // after a stream sync: throws if a peer exchange timed out   // records the next event of a start/stop pair when profiling is on
 
 #define VM_API_BEGIN(ctxexpr)          \
     vm_ctx* ctx__ = (ctxexpr);         \

@@ -29,6 +29,8 @@ struct PassParams {
     int rep_log2;             // log2(replicas per warp (PRIV/MATCH) or per CTA (ATOMIC))
     int ncols;                // row length of the per-CTA partial output (n_basis + VM_DIAG_COLS)
     int diag;                 // k_vp_push: accumulate sum w v^2, sum w v, sum w
+    int uw;                   // all particles carry the weight w0: the weight array is not read
+    double w0;
 };
 
 // ---------------------------------------------------------------- gather ----
@@ -122,7 +124,7 @@ k_vp_pass(double* __restrict__ x, double* __restrict__ v, const double* __restri
             if (q < npairs) {
                 buf[u].x = ld_stream2(x + 2 * (size_t)q);
                 if (MODE != MODE_DEPOSIT) buf[u].v = ld_stream2(v + 2 * (size_t)q);
-                buf[u].w = ld_stream2(w + 2 * (size_t)q);
+                buf[u].w = P.uw ? make_double2(P.w0, P.w0) : ld_stream2(w + 2 * (size_t)q);
             }
         }
     };
@@ -170,7 +172,7 @@ k_vp_pass(double* __restrict__ x, double* __restrict__ v, const double* __restri
         if (active) {
             xp = x[P.n - 1];
             if (MODE != MODE_DEPOSIT) vp = v[P.n - 1];
-            wp = w[P.n - 1];
+            wp = P.uw ? P.w0 : w[P.n - 1];
         }
         process<K, VAR, MODE, SPLIT, POW2>(xp, vp, wp, active, P, dsh, wg, rep, lane);
         if (active && MODE != MODE_DEPOSIT) {
@@ -466,6 +468,7 @@ static void pass_with_deposit(vm_field* f, vm_particles* p, int pass_mode, int d
     P.n = p->n;
     P.rep_log2 = pl.rep_log2;
     P.ncols = ncols;
+    P.uw = vm_particles_uniform_weight(p, &P.w0) ? 1 : 0;
     FinishParams F{};
     F.mode = FINISH_NONE;
     double* out;

@@ -69,7 +69,7 @@ template <int K, int VAR>
 __global__ void __launch_bounds__(1024, 1)
 k_v_deposit(const double* __restrict__ v, const double* __restrict__ w, long np, VCell m,
             const double* __restrict__ cellpoly, int npar, int rep_log2, double* __restrict__ out,
-            const FinishParams F)
+            const FinishParams F, int uw, double w0)
 {
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -96,7 +96,10 @@ k_v_deposit(const double* __restrict__ v, const double* __restrict__ w, long np,
         for (int u = 0; u < U; ++u) {
             const unsigned q = q0 + u * stride;
             bw[u] = make_double2(0., 0.);
-            if (q < npairs) { bv[u] = ld_stream2(v + 2 * (size_t)q); bw[u] = ld_stream2(w + 2 * (size_t)q); }
+            if (q < npairs) {
+                bv[u] = ld_stream2(v + 2 * (size_t)q);
+                bw[u] = uw ? make_double2(w0, w0) : ld_stream2(w + 2 * (size_t)q);
+            }
         }
     };
     auto work = [&](double2 (&bv)[U], double2 (&bw)[U], unsigned q0) {
@@ -119,7 +122,7 @@ k_v_deposit(const double* __restrict__ v, const double* __restrict__ w, long np,
     }
     if ((np & 1) && blockIdx.x == 0 && warp == 0) {
         const bool active = (lane == 0);
-        vdeposit_one<K, VAR>(active ? v[np - 1] : 0.0, active ? w[np - 1] : 0.0, active, m, cellpoly, wg, npar,
+        vdeposit_one<K, VAR>(active ? v[np - 1] : 0.0, active ? (uw ? w0 : w[np - 1]) : 0.0, active, m, cellpoly, wg, npar,
                              rep_log2, rep, lane);
     }
     flush_grid<VAR>(grid, scratch, out, npar, 0, rep_log2, nwarps, npar);
@@ -202,6 +205,8 @@ struct StageParams {
     double* kout;      // k_s, or nullptr on the last stage
     double* qout;      // q_next for the moments pass (nullptr: not needed); on the last stage this is v itself
     double dt, nu;
+    int uw;            // uniform particle weight w0: the weight array is not read
+    double w0;
 };
 
 template <int K, int VAR, int STAGE>
@@ -260,7 +265,7 @@ k_lb_stage(const double* v, const double* __restrict__ w, long np, VCell m, cons
         double2 vv = make_double2(0., 0.), ww = vv, a = vv, b = vv, c = vv;
         if (active) {
             vv = ld_stream2(v + 2 * (size_t)q);
-            ww = ld_stream2(w + 2 * (size_t)q);
+            ww = S.uw ? make_double2(S.w0, S.w0) : ld_stream2(w + 2 * (size_t)q);
             if (STAGE >= 2) a = ld_stream2(S.k1 + 2 * (size_t)q);
             if (STAGE >= 3) b = ld_stream2(S.k2 + 2 * (size_t)q);
             if (STAGE >= 4) c = ld_stream2(S.k3 + 2 * (size_t)q);
@@ -277,7 +282,7 @@ k_lb_stage(const double* v, const double* __restrict__ w, long np, VCell m, cons
         const bool active = (lane == 0);
         const long p = np - 1;
         double ks = 0., qn = 0.;
-        one(active ? v[p] : 0.0, active ? w[p] : 0.0, (active && STAGE >= 2) ? S.k1[p] : 0.0,
+        one(active ? v[p] : 0.0, active ? (S.uw ? S.w0 : w[p]) : 0.0, (active && STAGE >= 2) ? S.k1[p] : 0.0,
             (active && STAGE >= 3) ? S.k2[p] : 0.0, (active && STAGE >= 4) ? S.k3[p] : 0.0, active, ks, qn);
         if (active) {
             if (STAGE < 4) S.kout[p] = ks;
@@ -550,7 +555,7 @@ void launch_vdep_inst(vm_vspline* s, const DepositPlan& pl, const double* v, con
         conf = pl.smem;
     }
     k_v_deposit<K, VAR><<<pl.grid, pl.threads, pl.smem, ctx->stream>>>(v, w, np, vcell(s), s->cellpoly, s->npar,
-                                                                      pl.rep_log2, out, F);
+                                                                      pl.rep_log2, out, F, s->uw, s->w0);
     VM_LAUNCHED(ctx);
 }
 
@@ -712,6 +717,7 @@ void check_pair(vm_vspline* s, vm_particles* p, const char* who)
 {
     if (!s || !p) throw vm_error(VM_ERR_INVALID, std::string(who) + ": NULL handle");
     if (s->ctx != p->ctx) throw vm_error(VM_ERR_INVALID, std::string(who) + ": spline and particles belong to different contexts");
+    s->uw = vm_particles_uniform_weight(p, &s->w0) ? 1 : 0;   // one weight for all particles: w is not streamed
 }
 
 }  // namespace
@@ -968,6 +974,7 @@ int vm_lb_rk438_run(vm_vspline* s, vm_particles* p, double dt, int nsteps, doubl
                 S.a1 = a1; S.a2 = a2; S.a3 = a3;
                 S.c1 = c1; S.c2 = c2; S.c3 = c3; S.cs = cs;
                 S.kout = kout; S.dt = dt; S.nu = nu;
+                S.uw = s->uw; S.w0 = s->w0;
                 S.qout = (conservative || qout == p->v) ? qout : nullptr;   // LB needs no stored stage state
                 VDepSetup d = vdep_setup(s, (int)extra);
                 if (d.pl.var == VAR_ATOMIC) throw vm_error(VM_ERR_UNSUPPORTED, "fused RK438 stage: no atomic deposit variant");
