@@ -12,7 +12,9 @@ A "step" = one Strang step: E gather -> kick -> drift -> charge deposition -> al
 `value`  : particles resident in HBM, K steps timed with CUDA events on the library's stream.
 `e2e`    : same K steps through the host API with HOST (pinned) particle arrays: upload of x,v,w,
            K steps with a [W,K,M] diagnostics read-back, download of x,v -- all inside the timed region.
-`roofline`: the fused push+deposit kernel, 40 algorithmic bytes per particle per launch, timed per
+`roofline`: the fused push+deposit kernel, 32 algorithmic bytes per particle per launch (read x,v; write x,v;
+           the uniform particle weight of this workload is a kernel parameter -- 40 B with `--general-weights`,
+           which streams the weight array as for per-particle weights), timed per
            launch with CUDA event brackets over a second run of the same K steps (the brackets defeat
            the programmatic-dependent-launch overlap, so they stay out of the `value` region).
 """
