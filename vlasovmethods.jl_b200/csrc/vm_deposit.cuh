@@ -93,48 +93,58 @@ __device__ __forceinline__ void scatter(double* __restrict__ wg, int rep_log2, i
 }
 
 // Sum all replica copies of every row in a fixed order (ghost rows folded onto rows 0..ghost-1) and
-// emit the CTA's partial row.
+// emit the CTA's partial row.  Bank-conflict-free in both phases (the first version summed with a
+// 256-byte stride across lanes: 16-way conflicts, 10 us per launch):
+//   phase 1  element-wise sum of the per-warp grids into warp 0's grid (consecutive threads, consecutive words)
+//   phase 2  one warp per group of 32/R rows: lanes read 32 consecutive words and the R replicas of each row
+//            are combined with a segmented xor butterfly
 template <int VAR>
-__device__ __forceinline__ void flush_grid(const double* __restrict__ grid, double* __restrict__ scratch,
+__device__ __forceinline__ void flush_grid(double* __restrict__ grid, double* __restrict__ scratch,
                                            double* __restrict__ out, int n, int ghost, int rep_log2, int nwarps,
                                            int ncols)
 {
-    const int T = blockDim.x;
-    const int gsz = (n + ghost) << rep_log2;
-    const int ncopies = (VAR == VAR_ATOMIC) ? (1 << rep_log2) : (nwarps << rep_log2);
+    const int T = blockDim.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int rows = n + ghost;
+    const int gsz = rows << rep_log2;
     const int R = 1 << rep_log2;
     __syncthreads();
-    int P = 1;
-    while (2 * P * n <= T && 2 * P <= ncopies) P *= 2;   // P partial sums per index
-    auto row_sum = [&](int i, int c0, int cstep) {
-        double s = 0.0;
-        for (int c = c0; c < ncopies; c += cstep) {
-            const int wq = c >> rep_log2, r = c & (R - 1);
-            s += grid[(VAR == VAR_ATOMIC ? 0 : wq * gsz) + (i << rep_log2) + r];
+    if (VAR != VAR_ATOMIC) {                       // phase 1 (the atomic variant has a single per-CTA grid)
+        for (int e = t; e < gsz; e += T) {
+            double s = grid[e];
+            for (int wq = 1; wq < nwarps; ++wq) s += grid[wq * gsz + e];
+            grid[e] = s;
         }
-        if (i < ghost)
-            for (int c = c0; c < ncopies; c += cstep) {
-                const int wq = c >> rep_log2, r = c & (R - 1);
-                s += grid[(VAR == VAR_ATOMIC ? 0 : wq * gsz) + ((n + i) << rep_log2) + r];
-            }
-        return s;
-    };
-    if (P > 1) {                                         // n * P <= T: one trip
-        const int t = threadIdx.x;
-        if (t < n * P) scratch[(t / n) * n + (t % n)] = row_sum(t % n, t / n, P);
         __syncthreads();
-        if (t < n) {
-            double s = 0.0;
-            for (int part = 0; part < P; ++part) s += scratch[part * n + t];
-            if (VAR == VAR_ATOMIC) atomicAdd(out + t, s);
-            else out[(size_t)blockIdx.x * ncols + t] = s;
+    }
+    // phase 2: row totals into scratch[0 .. rows)   (rows <= blockDim.x is not required: scratch is reused in chunks)
+    const int rows_per_warp = 32 >> rep_log2;       // rows covered by one 32-word read
+    for (int base = 0; base < rows; base += T) {    // chunk of up to T rows (one trip unless rows > blockDim.x)
+        const int chunk_rows = min(rows - base, T);
+        for (int g = warp * rows_per_warp; g < chunk_rows; g += (T >> 5) * rows_per_warp) {
+            const int row = base + g + (lane >> rep_log2);
+            double s = (g + (lane >> rep_log2) < chunk_rows) ? grid[((base + g) << rep_log2) + lane] : 0.0;
+            for (int o = R >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(VM_FULL_MASK, s, o);
+            if ((lane & (R - 1)) == 0 && g + (lane >> rep_log2) < chunk_rows) scratch[row - base] = s;
         }
-    } else {
-        for (int i = threadIdx.x; i < n; i += T) {
-            const double s = row_sum(i, 0, 1);
+        __syncthreads();
+        // fold the ghost rows and emit: real row i gets ghost row n + i (i < ghost); needs both in this chunk or
+        // a second look-up, so ghost rows are read straight from the replica sums when they fall outside
+        for (int i = base + t; i < min(base + chunk_rows, n); i += T) {
+            double s = scratch[i - base];
+            if (i < ghost) {
+                const int gr = n + i;               // ghost row index
+                double gsum;
+                if (gr >= base && gr < base + chunk_rows) gsum = scratch[gr - base];
+                else {
+                    gsum = 0.0;
+                    for (int r = 0; r < R; ++r) gsum += grid[(gr << rep_log2) + r];
+                }
+                s += gsum;
+            }
             if (VAR == VAR_ATOMIC) atomicAdd(out + i, s);
             else out[(size_t)blockIdx.x * ncols + i] = s;
         }
+        __syncthreads();
     }
 }
 
@@ -196,6 +206,11 @@ __device__ __forceinline__ void finish_last_cta(const FinishParams& F, const dou
     if (!s_last) return;
     __threadfence();
     const int T = blockDim.x, t = threadIdx.x;
+    double* r_sh = sm_a;            // rhs - mean
+    double* phi_sh = sm_a + n;
+    double* g_sh = sm_a + 2 * n + 1;   // pseudo-inverse kernel G staged in shared memory: the convolution below
+                                       // must not chase n dependent global loads (measured: 5 us of a 17 us step floor)
+    if ((F.mode == FINISH_REDUCE_SOLVE || F.mode == FINISH_EXCHANGE_SOLVE) && t < n) g_sh[t] = __ldg(F.G + t);
     int P = 1;
     while (2 * P * n <= T && 2 * P <= nrows) P *= 2;
     if (t < n * P) {
@@ -214,8 +229,6 @@ __device__ __forceinline__ void finish_last_cta(const FinishParams& F, const dou
         scratch[part * n + i] = s;
     }
     __syncthreads();
-    double* r_sh = sm_a;            // rhs - mean
-    double* phi_sh = sm_a + n;
     if (t < n) {
         double s = 0.0;
         for (int part = 0; part < P; ++part) s += scratch[part * n + t];
@@ -245,8 +258,14 @@ __device__ __forceinline__ void finish_last_cta(const FinishParams& F, const dou
         }
         __syncthreads();
         if (t < n) {
+            double vals[VM_MAX_PEERS];               // all loads in flight first, then the sum in rank order
+#pragma unroll
+            for (int r = 0; r < VM_MAX_PEERS; ++r)
+                vals[r] = (r < F.nranks) ? ld_volatile_f64(F.inbox + (size_t)(set * VM_MAX_PEERS + r) * VM_XSLOT + t) : 0.0;
             double s = 0.0;
-            for (int r = 0; r < F.nranks; ++r) s += ld_volatile_f64(F.inbox + (size_t)(set * VM_MAX_PEERS + r) * VM_XSLOT + t);
+#pragma unroll
+            for (int r = 0; r < VM_MAX_PEERS; ++r)
+                if (r < F.nranks) s += vals[r];
             F.rhs[t] = s;
             r_sh[t] = s;
         }
@@ -268,7 +287,7 @@ __device__ __forceinline__ void finish_last_cta(const FinishParams& F, const dou
             double a = 0.0;
             int idx = t;             // G[(t - j) mod n]
             for (int j = 0; j < n; ++j) {
-                a = fma(__ldg(F.G + idx), r_sh[j], a);
+                a = fma(g_sh[idx], r_sh[j], a);
                 idx = (idx == 0) ? n - 1 : idx - 1;
             }
             phi_sh[t] = a;
