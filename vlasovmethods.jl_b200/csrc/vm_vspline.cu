@@ -296,6 +296,7 @@ k_lb_stage(const double* v, const double* __restrict__ w, long np, VCell m, cons
 // Streaming helper: each thread handles U pairs (4 particles for U = 2) per iteration, all loads issued
 // before any use, so that enough bytes are in flight for these low-byte passes.
 #define VM_STREAM_PAIRS 2
+#define VM_MOMENT_PAIRS 4      // the 8 B/particle moments pass needs more bytes in flight per thread
 
 // five unweighted particle sums: [sum f, sum v f, sum v^2 f, sum f', sum v f']
 // mom = [5 sums, A1, A2]; with `ticket` != nullptr the last CTA to finish sums the per-CTA rows in the
@@ -327,7 +328,7 @@ k_v_moments(const double* __restrict__ v, long np, VCell m, const double* __rest
         s[3] += df;
         s[4] = fma(vp, df, s[4]);
     };
-    constexpr int U = VM_STREAM_PAIRS;
+    constexpr int U = VM_MOMENT_PAIRS;
     const long npairs = np >> 1;
     const long stride = (long)gridDim.x * blockDim.x;
     const long gtid = (long)blockIdx.x * blockDim.x + threadIdx.x;
