@@ -296,7 +296,7 @@ k_lb_stage(const double* v, const double* __restrict__ w, long np, VCell m, cons
 // Streaming helper: each thread handles U pairs (4 particles for U = 2) per iteration, all loads issued
 // before any use, so that enough bytes are in flight for these low-byte passes.
 #define VM_STREAM_PAIRS 2
-#define VM_MOMENT_PAIRS 4      // the 8 B/particle moments pass needs more bytes in flight per thread
+#define VM_MOMENT_PAIRS 2      // (4 pairs in flight measured no faster: the pass is not load-latency bound)
 
 // five unweighted particle sums: [sum f, sum v f, sum v^2 f, sum f', sum v f']
 // mom = [5 sums, A1, A2]; with `ticket` != nullptr the last CTA to finish sums the per-CTA rows in the
