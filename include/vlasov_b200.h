@@ -57,6 +57,7 @@ int vm_abi_version(void);
 
 /* Create a context on CUDA device `device` (ordinal). */
 int vm_ctx_create(int device, vm_ctx** out);
+/* Every particles / field / vspline handle created on a context must be destroyed before the context. */
 int vm_ctx_destroy(vm_ctx* ctx);
 const char* vm_last_error(vm_ctx* ctx);
 /* Block until all work enqueued on the context has finished. */

@@ -6,6 +6,7 @@ opaque handles and convert numpy arrays at the boundary.
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 
 import numpy as np
 
@@ -24,12 +25,17 @@ class Context:
 
     def __init__(self, device: int = 0):
         self._h = C.c_void_p()
+        self._children = weakref.WeakSet()      # particles / fields / splines created on this context
         L.check(L.lib().vm_ctx_create(int(device), C.byref(self._h)))
         self.device = int(device)
 
     # -- lifetime ---------------------------------------------------------
     def close(self):
+        """Destroy the context.  The C ABI requires every handle created on a context to be destroyed
+        before the context itself; the wrappers register themselves here so that order is kept."""
         if getattr(self, "_h", None) is not None and self._h.value:
+            for child in list(self._children):
+                child.close()
             L.lib().vm_ctx_destroy(self._h)
             self._h = C.c_void_p()
 
@@ -140,6 +146,7 @@ class DeviceParticles:
         self.n = int(n)
         self._h = C.c_void_p()
         L.check(L.lib().vm_particles_create(ctx._h, self.n, C.byref(self._h)), ctx._h)
+        ctx._children.add(self)
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:
@@ -205,6 +212,7 @@ class DeviceField:
         self.a, self.b, self.order, self.n, self.shift = float(a), float(b), int(order), int(n_basis), int(index_shift)
         self._h = C.c_void_p()
         L.check(L.lib().vm_field_create(ctx._h, self.a, self.b, self.order, self.n, self.shift, C.byref(self._h)), ctx._h)
+        ctx._children.add(self)
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:
@@ -301,6 +309,7 @@ class DeviceVSpline:
         self.a, self.b, self.nknots, self.order, self.bc = float(vmin), float(vmax), int(nknots), int(order), int(bc)
         self._h = C.c_void_p()
         L.check(L.lib().vm_vspline_create(ctx._h, self.a, self.b, self.nknots, self.order, self.bc, C.byref(self._h)), ctx._h)
+        ctx._children.add(self)
         self.nv = L.lib().vm_vspline_size(self._h)
 
     def close(self):
