@@ -51,6 +51,33 @@ def test_deposit_matches_oracle(vm, oracle, ctx, rng, k, n):
         assert abs(got.sum() - w.sum()) <= 1e-13 * w.sum()
 
 
+@pytest.mark.parametrize("k,n", [(4, 4), (4, 5), (3, 3), (5, 6), (2, 2), (6, 7)])
+def test_tiny_grids_where_the_stencil_wraps(vm, oracle, ctx, rng, k, n):
+    """n_basis barely above the spline order: a particle's K basis functions wrap around the period and the
+    circulant stiffness stencil aliases onto itself."""
+    a, b = 0.0, 1.0
+    npart = 5001
+    x, v, w = make_particles(rng, npart, a, b, spread=2.0)
+    fld = vm.DeviceField(ctx, a, b, k, n, 0)
+    p = vm.DeviceParticles(ctx, npart)
+    p.upload(x, v, w)
+    fld.deposit(p, 0); fld.solve()
+    S = oracle.periodic_stiffness(a, b, n, k, 0)
+    rhs = oracle.deposit_periodic(x, w, a, b, n, k, 0)
+    phi = oracle.poisson_solve(S, rhs)
+    assert relmax(fld.rhs, rhs) <= RTOL
+    assert relmax(fld.stiffness_matrix(), S) <= 1e-12
+    assert relmax(fld.coefficients, phi) <= 1e-11
+    assert relmax(fld.gather_E(p, 1.0), -oracle.eval_dphi(x, a, b, n, k, 0, phi)) <= 1e-11
+    assert abs(fld.energy() - oracle.field_energy(S, phi)) <= 1e-10 * abs(oracle.field_energy(S, phi))
+    xo, vo = x.copy(), v.copy()
+    dref = oracle.integrate_vp(xo, vo, w, 0.05, 1.0, 4, 2, a, b, n, k, 0, S)
+    diag = fld.run(p, 0.05, 4, 2, 0, 1.0)
+    xg, vg, _ = p.download(w=False)
+    assert np.max(np.abs(xg - xo)) <= 1e-10 and np.max(np.abs(vg - vo)) <= 1e-10
+    assert np.allclose(diag[:, :3], dref, rtol=1e-9, atol=1e-12)
+
+
 def test_deposit_deterministic_bitwise(vm, ctx, rng):
     a, b, n, k = 0.0, 1.0, 128, 4
     npart = 400003
