@@ -281,6 +281,12 @@ __device__ __forceinline__ void st_stream(double* p, double v)
     asm volatile("st.global.cs.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
 }
 
+// L2 prefetch of the 128-byte line holding p (no register is tied up, unlike a software-pipelined load)
+__device__ __forceinline__ void prefetch_l2(const void* p)
+{
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
 // fixed-order warp tree sum (xor butterfly: every lane ends with the same bits)
 __device__ __forceinline__ double warp_sum(double v)
 {

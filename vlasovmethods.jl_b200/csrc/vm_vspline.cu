@@ -262,6 +262,16 @@ k_lb_stage(const double* v, const double* __restrict__ w, long np, VCell m, cons
     unsigned q = gtid;
     for (unsigned it = 0; it < iters; ++it, q += stride) {
         const bool active = q < npairs;
+        // the pass has no registers left for software-pipelined loads: pull the next iteration's lines into L2
+        // (one lane per 128-byte line = 8 pairs)
+        if ((lane & 7) == 0 && q + stride < npairs) {
+            const size_t e = 2 * (size_t)(q + stride);
+            prefetch_l2(v + e);
+            if (!S.uw) prefetch_l2(w + e);
+            if (STAGE >= 2) prefetch_l2(S.k1 + e);
+            if (STAGE >= 3) prefetch_l2(S.k2 + e);
+            if (STAGE >= 4) prefetch_l2(S.k3 + e);
+        }
         double2 vv = make_double2(0., 0.), ww = vv, a = vv, b = vv, c = vv;
         if (active) {
             vv = ld_stream2(v + 2 * (size_t)q);
