@@ -433,8 +433,11 @@ k_v_rhs(const double* __restrict__ v, long np, VCell m, const double* __restrict
     for (long base = gtid; base < npairs; base += U * stride) {
         double2 c[U];
 #pragma unroll
-        for (int u = 0; u < U; ++u)
-            if (base + u * stride < npairs) c[u] = ld_stream2(v + 2 * (base + u * stride));
+        for (int u = 0; u < U; ++u) {
+            const long q = base + u * stride;
+            if (q < npairs) c[u] = ld_stream2(v + 2 * q);
+            if ((threadIdx.x & 7) == 0 && q + U * stride < npairs) prefetch_l2(v + 2 * (q + U * stride));
+        }
 #pragma unroll
         for (int u = 0; u < U; ++u)
             if (base + u * stride < npairs)
