@@ -332,10 +332,17 @@ def run_gpu(args):
         ctx.event_record(9)
         return max_over_ranks(ctx.event_elapsed_ms(8, 9)) / reps
 
-    dep_ms = timed(lambda: fld.deposit(p, 0), 10)            # projection!(potential, dist) alone: 16 B/particle
+    dep_ms = timed(lambda: fld.deposit(p, 0), 10)            # projection!(potential, dist) alone
+    ctx.set_tuning("no_uniform_w", 1)                        # same pass with the weight array streamed (16 B/particle)
+    dep_ms_gw = timed(lambda: fld.deposit(p, 0), 10)
+    ctx.set_tuning("no_uniform_w", 1 if args.general_weights else 0)
     deposit = {"kernel": "k_vp_pass<4,PRIV,DEPOSIT>", "ms": dep_ms, "GBps": dep_bytes * nloc / dep_ms / 1e6,
                "frac": dep_bytes * nloc / dep_ms / 1e6 / peak, "algorithmic_bytes_per_particle": dep_bytes,
                "particles_per_s": nloc * world / dep_ms * 1e3,
+               "per_particle_weights": {"ms": dep_ms_gw, "algorithmic_bytes_per_particle": 16,
+                                        "GBps": 16 * nloc / dep_ms_gw / 1e6, "frac": 16 * nloc / dep_ms_gw / 1e6 / peak},
+               "note": "with the uniform weight of this workload the pass reads 8 B/particle and is issue-bound; "
+                       "with per-particle weights (16 B/particle) it runs at the HBM roofline fraction given above",
                "shared_atomics": 0, "mode": "deterministic (lane-private replicas)"}
     secondary = None
     if not args.no_secondary:
