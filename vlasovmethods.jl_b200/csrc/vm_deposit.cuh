@@ -253,7 +253,7 @@ __device__ __forceinline__ void finish_last_cta(const FinishParams& F, const dou
             const unsigned long long* flag = (const unsigned long long*)(F.inbox + VM_XFLAG_OFF) + set * VM_MAX_PEERS + t;
             const long long t0 = clock64();
             while (ld_acquire_sys_u64(flag) < F.seq) {
-                if (clock64() - t0 > (1ll << 34)) { atomicExch(F.err, 1u); break; }   // ~8 s: give up, host reports
+                if (clock64() - t0 > (1ll << 35)) { atomicExch(F.err, 1u); break; }   // ~17 s: give up, host reports
             }
         }
         __syncthreads();
