@@ -113,6 +113,36 @@ def test_deposit_all_replica_variants(vm, oracle, rng, replicas):
     assert relmax(fld.rhs, ref) <= RTOL
     fld.close(); p.close(); c.close()
 
+@pytest.mark.parametrize("n,k", [(24, 4), (32, 4), (64, 4), (100, 4), (128, 4), (64, 3), (40, 5), (128, 6), (64, 2)])
+@pytest.mark.parametrize("tune", [{}, {"pairs": 1, "no_repg": 1, "priv_min_warps": 12}, {"pairs": 4}, {"pairs": 8, "no_repg": 1}],
+                         ids=["auto", "round1", "pairs4", "pairs8-plain-table"])
+def test_pipeline_depths_match_oracle(vm, oracle, rng, n, k, tune):
+    """Mid-size meshes run the lane-private passes with few warps: every software-pipeline depth (`pairs`), the
+    two-phase batch form of the deep tiers and the 16-fold conflict-free gather table (`no_repg` switches it
+    off) against the oracle: deposit, uniform and per-particle weights, fused steps.  Enough particles for
+    several loop iterations per thread, odd count."""
+    c = vm.Context(0)
+    for key, val in tune.items():
+        c.set_tuning(key, val)
+    kappa = 0.3
+    a, b = 0.0, 2 * math.pi / kappa
+    npart = 1_200_001
+    x = rng.uniform(a, b, npart); v = rng.standard_normal(npart)
+    fld = vm.DeviceField(c, a, b, k, n, 0)
+    p = vm.DeviceParticles(c, npart)
+    S = oracle.periodic_stiffness(a, b, n, k, 0)
+    for w in (np.full(npart, (b - a) / npart), rng.uniform(0.5, 1.5, npart) * (b - a) / npart):
+        p.upload(x, v, w)
+        fld.deposit(p, 0)
+        assert relmax(fld.rhs, oracle.deposit_periodic(x, w, a, b, n, k, 0)) <= RTOL
+        xo, vo = x.copy(), v.copy()
+        dref = oracle.integrate_vp(xo, vo, w, 0.1, 1.0, 3, 3, a, b, n, k, 0, S)
+        diag = fld.run(p, 0.1, 3, 3, 0, 1.0)
+        xg, vg, _ = p.download(w=False)
+        assert np.max(np.abs(xg - xo)) <= 1e-11 and np.max(np.abs(vg - vo)) <= 1e-11
+        assert np.allclose(diag[:, :3], dref, rtol=1e-10, atol=1e-13)
+    fld.close(); p.close(); c.close()
+
 
 def test_deposit_edge_cases(vm, oracle, ctx, rng):
     a, b, n, k = 0.0, 1.0, 16, 3
@@ -413,7 +443,7 @@ def test_rk438_fused_equals_unfused(vm, rng):
     kernels walk the particles with different strides), so agreement is to rounding, and each driver
     is bit-reproducible on its own."""
     a, b, nknots, k = -10.0, 10.0, 41, 4
-    npart = 50001
+    npart = 500001           # several iterations per thread: the software-pipelined stage loop gets exercised
     v = np.concatenate([rng.standard_normal(npart // 2) + 2.0, rng.standard_normal(npart - npart // 2) - 2.0])
     w = np.full(npart, 1.0 / npart)
     res = {}

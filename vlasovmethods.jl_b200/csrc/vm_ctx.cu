@@ -241,6 +241,15 @@ int vm_ctx_set_tuning(vm_ctx* ctx, const char* key, int value)
         VM_REQUIRE(value == 0 || (value >= 1 && value <= 32 && (value & (value - 1)) == 0), "replicas must be a power of two <= 32");
         ctx->replicas = value;
     }
+    else if (k == "pairs") {          // pairs of particles in flight per thread in the lane-private passes (0 = auto)
+        VM_REQUIRE(value == 0 || value == 1 || value == 2 || value == 4 || value == 8, "pairs must be 0, 1, 2, 4 or 8");
+        ctx->pairs = value;
+    }
+    else if (k == "priv_min_warps") {  // fewest warps per SM for which the lane-private deposit is still chosen (0 = auto)
+        VM_REQUIRE(value >= 0 && value <= 32, "priv_min_warps out of range");
+        ctx->priv_min_warps = value;
+    }
+    else if (k == "no_repg") ctx->no_repg = value;   // 1: single (bank-conflicting) gather table in the fused pass (A/B)
     else if (k == "profile") ctx->profile = value;
     else if (k == "force_match") ctx->force_match = value;   // 1: MATCH.ANY grouping instead of xor rounds (A/B)
     else if (k == "no_uniform_w") ctx->no_uniform_w = value;   // 1: always stream per-particle weights (A/B)

@@ -333,6 +333,15 @@ struct DepositPlan {
 // preferred whenever at least VM_PRIV_MIN_WARPS warps fit; otherwise the match variant runs with as many
 // replicas per warp as fit next to 32 resident warps.
 #define VM_PRIV_MIN_WARPS 6
+#define VM_PRIV_MIN_WARPS_PUSH 6      // (12 before the deep-pipeline tiers: n_h = 128 now runs lane-private with 6 warps, 8 pairs each)
+
+// Pairs of particles each thread keeps in flight in the lane-private passes, given the resident threads per
+// SM the replica grids leave room for (measured, profiles/README.md): fewer warps -> deeper software pipeline.
+inline int vm_auto_pairs(bool deposit_only, int threads_per_sm)
+{
+    if (deposit_only) return threads_per_sm <= 256 ? 8 : (threads_per_sm <= 512 ? 4 : 2);
+    return threads_per_sm <= 192 ? 8 : (threads_per_sm <= 448 ? 4 : 1);
+}
 inline DepositPlan plan_deposit(vm_ctx* ctx, int n_real, int ghost, int extra_doubles, int mode,
                                 int priv_min_warps = VM_PRIV_MIN_WARPS)
 {

@@ -1,0 +1,309 @@
+// vm_pass.cuh -- the fused x-space particle pass (kernel template + launch machinery).
+//
+// Included by vm_pass_order.cu, which is compiled once per spline order (-DVM_PASS_ORDER=k: the
+// instantiations of one order per translation unit, so the orders build in parallel), and by vm_push.cu
+// for the pieces the other kernels share (PassParams, the field gather).
+#pragma once
+#include "vm_internal.cuh"
+#include "vm_deposit.cuh"
+
+enum { MODE_DEPOSIT = 0, MODE_PUSH_DEPOSIT = 1, MODE_DRIFT_DEPOSIT = 2 };
+
+struct PassParams {
+    CellMap map;
+    double kick, kick2;       // v += kick * phi'(x) ; v += kick2 * phi'(x)   (kick2 == 0: skipped)
+    double drift0;            // k_vp_push only: x += drift0 * v before the gather
+    double drift1, drift2;    // x += drift1 * v ; x += drift2 * v            (drift2 == 0: skipped)
+    long n;                   // particles
+    int rep_log2;             // log2(replicas per warp (PRIV/MATCH) or per CTA (ATOMIC))
+    int ncols;                // row length of the per-CTA partial output (n_basis + VM_DIAG_COLS)
+    int diag;                 // k_vp_push: accumulate sum w v^2, sum w v, sum w
+    int uw;                   // all particles carry the weight w0: the weight array is not read
+    int repg;                 // fused pass: the gather table is stored VM_GATHER_COPIES times (conflict-free reads)
+    double w0;
+};
+
+// ---------------------------------------------------------------- gather ----
+// dsh is the derivative-coefficient vector D extended periodically by K-2 entries (dsh[n+i] = D[i]),
+// so the K-1 reads at b0 .. b0+K-2 need no index wrap.
+//
+// REPG: the table is stored 16 times, entry m of copy c at dsh[m*16 + c], and lane l reads copy l & 15.  On
+// meshes with more than 16 cells two lanes of a half-warp often sit in cells whose table entries share a bank
+// (ncu, n_h = 32: 25 % of all shared-memory wavefronts of the fused pass were such conflicts, and the pass is
+// co-limited by the shared-memory data pipe); with one copy per bank pair every gather is conflict-free.
+#define VM_GATHER_COPIES 16
+template <int K, bool REPG = false>
+__device__ __forceinline__ double gather_dphi(const double* __restrict__ dsh, int b0, double xi)
+{
+    // phi'(x) = sum_{j<K-1} N^{K-1}_j(xi) * D[(b0 + j) mod n],  D_m = (phi_{m+1} - phi_m) / h
+    double Nd[K - 1 > 0 ? K - 1 : 1];
+    bspline_uniform<(K - 1 > 0 ? K - 1 : 1)>(xi, Nd);
+    constexpr int ST = REPG ? VM_GATHER_COPIES : 1;
+    const double* d = REPG ? dsh + b0 * VM_GATHER_COPIES + (threadIdx.x & (VM_GATHER_COPIES - 1)) : dsh + b0;
+    double s = 0.0;
+#pragma unroll
+    for (int j = 0; j < K - 1; ++j) s = fma(Nd[j], d[j * ST], s);
+    return s;
+}
+
+template <bool REPG = false>
+__device__ __forceinline__ void load_dcoef_ext(double* __restrict__ dsh, const double* __restrict__ dcoef, int n, int ext)
+{
+    if (REPG) {
+        for (int i = threadIdx.x; i < (n + ext) * VM_GATHER_COPIES; i += blockDim.x) {
+            const int m = i / VM_GATHER_COPIES;
+            dsh[i] = dcoef[m < n ? m : m - n];
+        }
+    } else {
+        for (int i = threadIdx.x; i < n + ext; i += blockDim.x) dsh[i] = dcoef[i < n ? i : i - n];
+    }
+}
+
+// doubles of dynamic shared memory the gather table of the fused pass takes
+inline size_t vm_gather_table_doubles(int n, int order, bool repg) { return (size_t)(n + order) * (repg ? VM_GATHER_COPIES : 1); }
+
+// --------------------------------------------------------- the fused pass ---
+// SPLIT: two half kicks (new-API Strang) instead of one.  The fused mode always applies the two
+// separately rounded half drifts of consecutive Strang steps (drift1 then drift2).
+// Phase A of a particle: everything up to the deposit weights (reads the read-only dcoef table only).
+template <int K, int MODE, bool SPLIT, bool POW2, bool REPG>
+__device__ __forceinline__ void prepare(double& xp, double& vp, double wp, const PassParams& P,
+                                        const double* __restrict__ dsh, int& b0, double (&val)[K])
+{
+    double xi;
+    constexpr bool CONV = (MODE == MODE_DEPOSIT);      // see cell_of: measured per mode
+    if (MODE == MODE_PUSH_DEPOSIT) {
+        cell_of<CONV, POW2>(P.map, xp, b0, xi);
+        const double dphi = gather_dphi<K, REPG>(dsh, b0, xi);
+        // literal (unfused) update order of s_acceleration!: v = v - dt * phi'
+        vp = __dadd_rn(vp, __dmul_rn(P.kick, dphi));
+        if (SPLIT) vp = __dadd_rn(vp, __dmul_rn(P.kick2, dphi));
+    }
+    if (MODE != MODE_DEPOSIT) xp = __dadd_rn(xp, __dmul_rn(P.drift1, vp));
+    if (MODE == MODE_PUSH_DEPOSIT) xp = __dadd_rn(xp, __dmul_rn(P.drift2, vp));
+    cell_of<CONV, POW2>(P.map, xp, b0, xi);
+    bspline_uniform_w<K>(xi, wp, val);                 // inactive lanes carry wp == 0
+}
+
+template <int K, int VAR, int MODE, bool SPLIT, bool POW2, bool REPG>
+__device__ __forceinline__ void process(double& xp, double& vp, double wp, bool active, const PassParams& P,
+                                        const double* __restrict__ dsh, double* __restrict__ wg, int rep, int lane)
+{
+    int b0;
+    double val[K];
+    prepare<K, MODE, SPLIT, POW2, REPG>(xp, vp, wp, P, dsh, b0, val);
+    scatter<K, VAR>(wg, P.rep_log2, rep, lane, b0, val, active);
+}
+
+template <int MODE>
+struct PairBuf {
+    double2 x, v, w;
+};
+
+// U = pairs of particles each thread keeps in flight per (half-)iteration, loads one iteration ahead.
+// MAXT = largest CTA this instantiation is launched with: the lane-private replica grids of mid-size
+// meshes leave room for few warps per SM (12 at n_h = 64), so those launches get the register budget of
+// the absent warps (65536 / MAXT per thread) and spend it on more pairs in flight -- bytes in flight per
+// SM, not resident warps, is what hides the HBM latency.
+// Pair indices are 32-bit (N < 2^32 particles per GPU).
+template <int K, int VAR, int MODE, int U, bool SPLIT, bool POW2, int MAXT, bool REPG>
+__global__ void __launch_bounds__(MAXT, 1)
+k_vp_pass(double* __restrict__ x, double* __restrict__ v, const double* __restrict__ w,
+          const double* __restrict__ dcoef, double* __restrict__ out, const PassParams P, const FinishParams F)
+{
+    extern __shared__ double smem[];
+    const int n = P.map.n;
+    constexpr int GHOST = K - 1;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    double* dsh = smem;
+    double* grid = smem + (MODE == MODE_PUSH_DEPOSIT ? (n + K) * (REPG ? VM_GATHER_COPIES : 1) : 0);
+    const int gsz = (n + GHOST) << P.rep_log2;
+    const int gtotal = (VAR == VAR_ATOMIC) ? gsz : gsz * nwarps;
+    double* scratch = grid + gtotal;
+    for (int i = threadIdx.x; i < gtotal; i += blockDim.x) grid[i] = 0.0;
+    // Programmatic dependent launch: everything above overlaps the previous kernel's tail (its last
+    // CTA is still reducing / exchanging / solving); nothing it wrote is read before this point.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (MODE == MODE_PUSH_DEPOSIT) load_dcoef_ext<REPG>(dsh, dcoef, n, K - 2 > 0 ? K - 2 : 0);
+    __syncthreads();
+    double* wg = (VAR == VAR_ATOMIC) ? grid : grid + warp * gsz;
+    const int rep = ((VAR == VAR_ATOMIC) ? warp : lane) & ((1 << P.rep_log2) - 1);
+
+    const unsigned npairs = (unsigned)(P.n >> 1);
+    const unsigned stride = gridDim.x * blockDim.x;
+    const unsigned gtid = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned chunk = U * stride;
+    const unsigned iters = (npairs + chunk - 1) / chunk;   // uniform trip count: the scatter is warp-collective
+
+    PairBuf<MODE> A[U], B[U];
+    auto load = [&](PairBuf<MODE> (&buf)[U], unsigned q0) {   // q0 = first pair of this thread's slice
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const unsigned q = q0 + u * stride;
+            buf[u].w = make_double2(0., 0.);            // out-of-range pairs deposit nothing
+            if (q < npairs) {
+                buf[u].x = ld_stream2(x + 2 * (size_t)q);
+                if (MODE != MODE_DEPOSIT) buf[u].v = ld_stream2(v + 2 * (size_t)q);
+                buf[u].w = P.uw ? make_double2(P.w0, P.w0) : ld_stream2(w + 2 * (size_t)q);
+            }
+        }
+    };
+    // Deep tiers (U >= 4, few resident warps) run two phases per batch of 2U particles: the compiler must assume
+    // that a replica-grid store may alias the next particle's read of the field table (both live in the dynamic
+    // shared array), so the particle-after-particle form serialises the dependency chains of consecutive
+    // particles -- which only many resident warps can hide.  Phase A (gather, push, cell, weights: reads only)
+    // is free to interleave all 2U particles; phase B applies the read-modify-writes in particle order, so the
+    // bits are those of the sequential form.  Measured: -6 % at n_h = 64, -10 % at n_h = 128; with 64 registers
+    // (full CTAs) and in the warp-collective collision variants the batch form is slower and not used.
+    auto work = [&](PairBuf<MODE> (&buf)[U], unsigned q0) {
+        if constexpr (VAR == VAR_PRIV && U >= 4) {
+            int b0[2 * U];
+            double val[2 * U][K];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                prepare<K, MODE, SPLIT, POW2, REPG>(buf[u].x.x, buf[u].v.x, buf[u].w.x, P, dsh, b0[2 * u], val[2 * u]);
+                prepare<K, MODE, SPLIT, POW2, REPG>(buf[u].x.y, buf[u].v.y, buf[u].w.y, P, dsh, b0[2 * u + 1], val[2 * u + 1]);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const bool active = (q0 + u * stride) < npairs;
+                scatter<K, VAR>(wg, P.rep_log2, rep, lane, b0[2 * u], val[2 * u], active);
+                scatter<K, VAR>(wg, P.rep_log2, rep, lane, b0[2 * u + 1], val[2 * u + 1], active);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const unsigned q = q0 + u * stride;
+                if (q < npairs && MODE != MODE_DEPOSIT) {
+                    st_stream2(x + 2 * (size_t)q, buf[u].x);
+                    if (MODE == MODE_PUSH_DEPOSIT) st_stream2(v + 2 * (size_t)q, buf[u].v);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const unsigned q = q0 + u * stride;
+                const bool active = q < npairs;
+                process<K, VAR, MODE, SPLIT, POW2, REPG>(buf[u].x.x, buf[u].v.x, buf[u].w.x, active, P, dsh, wg, rep, lane);
+                process<K, VAR, MODE, SPLIT, POW2, REPG>(buf[u].x.y, buf[u].v.y, buf[u].w.y, active, P, dsh, wg, rep, lane);
+                if (active && MODE != MODE_DEPOSIT) {
+                    st_stream2(x + 2 * (size_t)q, buf[u].x);
+                    if (MODE == MODE_PUSH_DEPOSIT) st_stream2(v + 2 * (size_t)q, buf[u].v);
+                }
+            }
+        }
+    };
+#pragma unroll
+    for (int u = 0; u < U; ++u) A[u].x = A[u].v = B[u].x = B[u].v = make_double2(0., 0.);
+    // q advances by `chunk` per iteration; npairs + 3*chunk < 2^32 is guaranteed by vm_particles_create
+    unsigned q = gtid;
+    load(A, q);
+    if (MODE == MODE_DEPOSIT) {
+        // 16 B/particle pass, issue-bound: unrolled twice over the two buffer sets (no register moves)
+        for (unsigned it = 0; it < iters; it += 2, q += 2 * chunk) {
+            load(B, q + chunk);
+            work(A, q);
+            load(A, q + 2 * chunk);
+            work(B, q + chunk);    // all-inactive when iters is odd (costs one idle half-iteration)
+        }
+    } else {
+        // 32-40 B/particle passes, HBM-bound: keeping the next pair's loads at the very top of the
+        // iteration measured 5 % faster than the unrolled form (ptxas sinks the loads otherwise)
+        for (unsigned it = 0; it < iters; ++it, q += chunk) {
+            load(B, q + chunk);
+            work(A, q);
+#pragma unroll
+            for (int u = 0; u < U; ++u) A[u] = B[u];
+        }
+    }
+    // let the next kernel of the stream start its prologue while this grid drains and finishes
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if ((P.n & 1) && blockIdx.x == 0 && warp == 0) {   // odd particle count: last particle, lane 0 of one warp
+        const bool active = (lane == 0);
+        double xp = 0., vp = 0., wp = 0.;
+        if (active) {
+            xp = x[P.n - 1];
+            if (MODE != MODE_DEPOSIT) vp = v[P.n - 1];
+            wp = P.uw ? P.w0 : w[P.n - 1];
+        }
+        process<K, VAR, MODE, SPLIT, POW2, REPG>(xp, vp, wp, active, P, dsh, wg, rep, lane);
+        if (active && MODE != MODE_DEPOSIT) {
+            x[P.n - 1] = xp;
+            if (MODE == MODE_PUSH_DEPOSIT) v[P.n - 1] = vp;
+        }
+    }
+    flush_grid<VAR>(grid, scratch, out, n, GHOST, P.rep_log2, nwarps, P.ncols);
+    if (VAR != VAR_ATOMIC && F.mode != FINISH_NONE) finish_last_cta(F, out, gridDim.x, n, grid, scratch);
+}
+
+// ================================================================ host ======
+template <int K, int VAR, int MODE, bool SPLIT, bool POW2, int U, int MAXT, bool REPG>
+void launch_pass_depth(vm_ctx* ctx, const DepositPlan& pl, double* x, double* v, const double* w,
+                       const double* dcoef, double* out, const PassParams& P, const FinishParams& F)
+{
+    static size_t configured[64] = {};   // per device: max dynamic smem already opted into for this instantiation
+    size_t& conf = configured[ctx->device & 63];
+    if (pl.smem > conf) {
+        VM_CUDA(cudaFuncSetAttribute(k_vp_pass<K, VAR, MODE, U, SPLIT, POW2, MAXT, REPG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+        conf = pl.smem;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(pl.grid);
+    cfg.blockDim = dim3(pl.threads);
+    cfg.dynamicSmemBytes = pl.smem;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // PDL: see griddepcontrol.wait in the kernel
+    attr[0].val.programmaticStreamSerializationAllowed = ctx->no_pdl ? 0 : 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    VM_CUDA(cudaLaunchKernelEx(&cfg, k_vp_pass<K, VAR, MODE, U, SPLIT, POW2, MAXT, REPG>, x, v, w, dcoef, out, P, F));
+    ++ctx->launches;
+}
+
+// Pairs in flight per thread.  Full CTAs (1024 threads per SM, 64 registers each) run the shallow loop; the
+// lane-private variant with fewer warps trades its spare registers for depth (vm_auto_pairs; `pairs` tuning
+// key: A/B override).  P.repg (lane-private fused pass on meshes with more than 16 cells): replicated gather table.
+template <int K, int VAR, int MODE, bool SPLIT, bool POW2>
+void launch_pass_inst(vm_ctx* ctx, const DepositPlan& pl, double* x, double* v, const double* w,
+                      const double* dcoef, double* out, const PassParams& P, const FinishParams& F)
+{
+    constexpr int U0 = (MODE == MODE_DEPOSIT) ? 2 : 1;
+    const int per_sm = pl.threads * (pl.grid / ctx->sm_count);      // resident threads per SM
+    if constexpr (VAR == VAR_PRIV) {
+        const int u = ctx->pairs > 0 ? ctx->pairs : vm_auto_pairs(MODE == MODE_DEPOSIT, per_sm);
+        if constexpr (MODE == MODE_DEPOSIT) {
+            if (u >= 8 && per_sm <= 256) return launch_pass_depth<K, VAR, MODE, SPLIT, POW2, 8, 256, false>(ctx, pl, x, v, w, dcoef, out, P, F);
+            if (u >= 4 && per_sm <= 512) return launch_pass_depth<K, VAR, MODE, SPLIT, POW2, 4, 512, false>(ctx, pl, x, v, w, dcoef, out, P, F);
+        } else if constexpr (MODE == MODE_DRIFT_DEPOSIT) {
+            if (u >= 8 && per_sm <= 192) return launch_pass_depth<K, VAR, MODE, SPLIT, POW2, 8, 192, false>(ctx, pl, x, v, w, dcoef, out, P, F);
+            if (u >= 4 && per_sm <= 448) return launch_pass_depth<K, VAR, MODE, SPLIT, POW2, 4, 448, false>(ctx, pl, x, v, w, dcoef, out, P, F);
+        } else if (P.repg) {
+            if (u >= 8 && per_sm <= 192) return launch_pass_depth<K, VAR, MODE, SPLIT, POW2, 8, 192, true>(ctx, pl, x, v, w, dcoef, out, P, F);
+            if (u >= 4 && per_sm <= 448) return launch_pass_depth<K, VAR, MODE, SPLIT, POW2, 4, 448, true>(ctx, pl, x, v, w, dcoef, out, P, F);
+            return launch_pass_depth<K, VAR, MODE, SPLIT, POW2, 1, 1024, true>(ctx, pl, x, v, w, dcoef, out, P, F);
+        }
+    }
+    if (P.repg) throw vm_error(VM_ERR_UNSUPPORTED, "internal: replicated gather table without the lane-private fused pass");
+    launch_pass_depth<K, VAR, MODE, SPLIT, POW2, U0, 1024, false>(ctx, pl, x, v, w, dcoef, out, P, F);
+}
+
+template <int K, int MODE>
+void launch_pass_var(vm_ctx* ctx, const DepositPlan& pl, double* x, double* v, const double* w,
+                     const double* dcoef, double* out, const PassParams& P, const FinishParams& F)
+{
+    const bool split = (MODE == MODE_PUSH_DEPOSIT) && P.kick2 != 0.0;
+    // the mask form of the periodic wrap is only specialised for the lane-private variant (small grids)
+    const bool pow2 = P.map.mask >= 0;
+#define VM_PASS_VAR(V, PW)                                                                               \
+    if (MODE == MODE_PUSH_DEPOSIT && split) launch_pass_inst<K, V, MODE, (MODE == MODE_PUSH_DEPOSIT), PW>(ctx, pl, x, v, w, dcoef, out, P, F); \
+    else launch_pass_inst<K, V, MODE, false, PW>(ctx, pl, x, v, w, dcoef, out, P, F)
+    switch (pl.var) {
+        case VAR_PRIV:
+            if (pow2) { VM_PASS_VAR(VAR_PRIV, true); } else { VM_PASS_VAR(VAR_PRIV, false); }
+            break;
+        case VAR_MATCH: VM_PASS_VAR(VAR_MATCH, false); break;
+        case VAR_XOR: VM_PASS_VAR(VAR_XOR, false); break;
+        default: VM_PASS_VAR(VAR_ATOMIC, false); break;
+    }
+#undef VM_PASS_VAR
+}

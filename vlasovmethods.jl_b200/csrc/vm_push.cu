@@ -15,174 +15,7 @@
 //   VAR_PRIV    32 replicas per warp (one per lane): no collisions possible, plain RMW
 //   VAR_MATCH   R < 32 replicas per warp: sort-by-cell segmented reduce inside the warp, leader RMW
 //   VAR_ATOMIC  warp-aggregated atomicAdd on a per-CTA grid + global RED flush (A/B reference)
-#include "vm_internal.cuh"
-#include "vm_deposit.cuh"
-
-enum { MODE_DEPOSIT = 0, MODE_PUSH_DEPOSIT = 1, MODE_DRIFT_DEPOSIT = 2 };
-
-struct PassParams {
-    CellMap map;
-    double kick, kick2;       // v += kick * phi'(x) ; v += kick2 * phi'(x)   (kick2 == 0: skipped)
-    double drift0;            // k_vp_push only: x += drift0 * v before the gather
-    double drift1, drift2;    // x += drift1 * v ; x += drift2 * v            (drift2 == 0: skipped)
-    long n;                   // particles
-    int rep_log2;             // log2(replicas per warp (PRIV/MATCH) or per CTA (ATOMIC))
-    int ncols;                // row length of the per-CTA partial output (n_basis + VM_DIAG_COLS)
-    int diag;                 // k_vp_push: accumulate sum w v^2, sum w v, sum w
-    int uw;                   // all particles carry the weight w0: the weight array is not read
-    double w0;
-};
-
-// ---------------------------------------------------------------- gather ----
-// dsh is the derivative-coefficient vector D extended periodically by K-2 entries (dsh[n+i] = D[i]),
-// so the K-1 reads at b0 .. b0+K-2 need no index wrap.
-template <int K>
-__device__ __forceinline__ double gather_dphi(const double* __restrict__ dsh, int b0, double xi)
-{
-    // phi'(x) = sum_{j<K-1} N^{K-1}_j(xi) * D[(b0 + j) mod n],  D_m = (phi_{m+1} - phi_m) / h
-    double Nd[K - 1 > 0 ? K - 1 : 1];
-    bspline_uniform<(K - 1 > 0 ? K - 1 : 1)>(xi, Nd);
-    const double* d = dsh + b0;
-    double s = 0.0;
-#pragma unroll
-    for (int j = 0; j < K - 1; ++j) s = fma(Nd[j], d[j], s);
-    return s;
-}
-
-__device__ __forceinline__ void load_dcoef_ext(double* __restrict__ dsh, const double* __restrict__ dcoef, int n, int ext)
-{
-    for (int i = threadIdx.x; i < n + ext; i += blockDim.x) dsh[i] = dcoef[i < n ? i : i - n];
-}
-
-// --------------------------------------------------------- the fused pass ---
-// SPLIT: two half kicks (new-API Strang) instead of one.  The fused mode always applies the two
-// separately rounded half drifts of consecutive Strang steps (drift1 then drift2).
-template <int K, int VAR, int MODE, bool SPLIT, bool POW2>
-__device__ __forceinline__ void process(double& xp, double& vp, double wp, bool active, const PassParams& P,
-                                        const double* __restrict__ dsh, double* __restrict__ wg, int rep, int lane)
-{
-    int b0;
-    double xi;
-    constexpr bool CONV = (MODE == MODE_DEPOSIT);      // see cell_of: measured per mode
-    if (MODE == MODE_PUSH_DEPOSIT) {
-        cell_of<CONV, POW2>(P.map, xp, b0, xi);
-        const double dphi = gather_dphi<K>(dsh, b0, xi);
-        // literal (unfused) update order of s_acceleration!: v = v - dt * phi'
-        vp = __dadd_rn(vp, __dmul_rn(P.kick, dphi));
-        if (SPLIT) vp = __dadd_rn(vp, __dmul_rn(P.kick2, dphi));
-    }
-    if (MODE != MODE_DEPOSIT) xp = __dadd_rn(xp, __dmul_rn(P.drift1, vp));
-    if (MODE == MODE_PUSH_DEPOSIT) xp = __dadd_rn(xp, __dmul_rn(P.drift2, vp));
-    cell_of<CONV, POW2>(P.map, xp, b0, xi);
-    double val[K];
-    bspline_uniform_w<K>(xi, wp, val);                 // inactive lanes carry wp == 0
-    scatter<K, VAR>(wg, P.rep_log2, rep, lane, b0, val, active);
-}
-
-template <int MODE>
-struct PairBuf {
-    double2 x, v, w;
-};
-
-// U = pairs of particles each thread keeps in flight per (half-)iteration, loads one iteration ahead.
-// Pair indices are 32-bit (N < 2^32 particles per GPU).
-template <int K, int VAR, int MODE, int U, bool SPLIT, bool POW2>
-__global__ void __launch_bounds__(1024, 1)
-k_vp_pass(double* __restrict__ x, double* __restrict__ v, const double* __restrict__ w,
-          const double* __restrict__ dcoef, double* __restrict__ out, const PassParams P, const FinishParams F)
-{
-    extern __shared__ double smem[];
-    const int n = P.map.n;
-    constexpr int GHOST = K - 1;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    double* dsh = smem;
-    double* grid = smem + (MODE == MODE_PUSH_DEPOSIT ? n + K : 0);
-    const int gsz = (n + GHOST) << P.rep_log2;
-    const int gtotal = (VAR == VAR_ATOMIC) ? gsz : gsz * nwarps;
-    double* scratch = grid + gtotal;
-    for (int i = threadIdx.x; i < gtotal; i += blockDim.x) grid[i] = 0.0;
-    // Programmatic dependent launch: everything above overlaps the previous kernel's tail (its last
-    // CTA is still reducing / exchanging / solving); nothing it wrote is read before this point.
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    if (MODE == MODE_PUSH_DEPOSIT) load_dcoef_ext(dsh, dcoef, n, K - 2 > 0 ? K - 2 : 0);
-    __syncthreads();
-    double* wg = (VAR == VAR_ATOMIC) ? grid : grid + warp * gsz;
-    const int rep = ((VAR == VAR_ATOMIC) ? warp : lane) & ((1 << P.rep_log2) - 1);
-
-    const unsigned npairs = (unsigned)(P.n >> 1);
-    const unsigned stride = gridDim.x * blockDim.x;
-    const unsigned gtid = blockIdx.x * blockDim.x + threadIdx.x;
-    const unsigned chunk = U * stride;
-    const unsigned iters = (npairs + chunk - 1) / chunk;   // uniform trip count: the scatter is warp-collective
-
-    PairBuf<MODE> A[U], B[U];
-    auto load = [&](PairBuf<MODE> (&buf)[U], unsigned q0) {   // q0 = first pair of this thread's slice
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const unsigned q = q0 + u * stride;
-            buf[u].w = make_double2(0., 0.);            // out-of-range pairs deposit nothing
-            if (q < npairs) {
-                buf[u].x = ld_stream2(x + 2 * (size_t)q);
-                if (MODE != MODE_DEPOSIT) buf[u].v = ld_stream2(v + 2 * (size_t)q);
-                buf[u].w = P.uw ? make_double2(P.w0, P.w0) : ld_stream2(w + 2 * (size_t)q);
-            }
-        }
-    };
-    auto work = [&](PairBuf<MODE> (&buf)[U], unsigned q0) {
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const unsigned q = q0 + u * stride;
-            const bool active = q < npairs;
-            process<K, VAR, MODE, SPLIT, POW2>(buf[u].x.x, buf[u].v.x, buf[u].w.x, active, P, dsh, wg, rep, lane);
-            process<K, VAR, MODE, SPLIT, POW2>(buf[u].x.y, buf[u].v.y, buf[u].w.y, active, P, dsh, wg, rep, lane);
-            if (active && MODE != MODE_DEPOSIT) {
-                st_stream2(x + 2 * (size_t)q, buf[u].x);
-                if (MODE == MODE_PUSH_DEPOSIT) st_stream2(v + 2 * (size_t)q, buf[u].v);
-            }
-        }
-    };
-#pragma unroll
-    for (int u = 0; u < U; ++u) A[u].x = A[u].v = B[u].x = B[u].v = make_double2(0., 0.);
-    // q advances by `chunk` per iteration; npairs + 3*chunk < 2^32 is guaranteed by vm_particles_create
-    unsigned q = gtid;
-    load(A, q);
-    if (MODE == MODE_DEPOSIT) {
-        // 16 B/particle pass, issue-bound: unrolled twice over the two buffer sets (no register moves)
-        for (unsigned it = 0; it < iters; it += 2, q += 2 * chunk) {
-            load(B, q + chunk);
-            work(A, q);
-            load(A, q + 2 * chunk);
-            work(B, q + chunk);    // all-inactive when iters is odd (costs one idle half-iteration)
-        }
-    } else {
-        // 32-40 B/particle passes, HBM-bound: keeping the next pair's loads at the very top of the
-        // iteration measured 5 % faster than the unrolled form (ptxas sinks the loads otherwise)
-        for (unsigned it = 0; it < iters; ++it, q += chunk) {
-            load(B, q + chunk);
-            work(A, q);
-#pragma unroll
-            for (int u = 0; u < U; ++u) A[u] = B[u];
-        }
-    }
-    // let the next kernel of the stream start its prologue while this grid drains and finishes
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    if ((P.n & 1) && blockIdx.x == 0 && warp == 0) {   // odd particle count: last particle, lane 0 of one warp
-        const bool active = (lane == 0);
-        double xp = 0., vp = 0., wp = 0.;
-        if (active) {
-            xp = x[P.n - 1];
-            if (MODE != MODE_DEPOSIT) vp = v[P.n - 1];
-            wp = P.uw ? P.w0 : w[P.n - 1];
-        }
-        process<K, VAR, MODE, SPLIT, POW2>(xp, vp, wp, active, P, dsh, wg, rep, lane);
-        if (active && MODE != MODE_DEPOSIT) {
-            x[P.n - 1] = xp;
-            if (MODE == MODE_PUSH_DEPOSIT) v[P.n - 1] = vp;
-        }
-    }
-    flush_grid<VAR>(grid, scratch, out, n, GHOST, P.rep_log2, nwarps, P.ncols);
-    if (VAR != VAR_ATOMIC && F.mode != FINISH_NONE) finish_last_cta(F, out, gridDim.x, n, grid, scratch);
-}
+#include "vm_pass.cuh"
 
 // ------------------------------------------- kick + drift without deposit ---
 template <int K>
@@ -332,64 +165,24 @@ __global__ void __launch_bounds__(512, 2) k_drift(double* __restrict__ x, const 
 }
 
 // ================================================================ host ======
+// one translation unit per spline order (vm_pass_order.cu)
+#define VM_DECL_PASS(k)                                                                                                   \
+    void vm_launch_pass_k##k(vm_ctx*, int, const DepositPlan&, double*, double*, const double*, const double*, double*, \
+                             const PassParams&, const FinishParams&);
+VM_DECL_PASS(2) VM_DECL_PASS(3) VM_DECL_PASS(4) VM_DECL_PASS(5) VM_DECL_PASS(6)
+#undef VM_DECL_PASS
+
 namespace {
 
-template <int K, int VAR, int MODE, bool SPLIT, bool POW2>
-void launch_pass_inst(vm_ctx* ctx, const DepositPlan& pl, double* x, double* v, const double* w,
-                      const double* dcoef, double* out, const PassParams& P, const FinishParams& F)
-{
-    constexpr int U = (MODE == MODE_DEPOSIT) ? 2 : 1;
-    static size_t configured[64] = {};   // per device: max dynamic smem already opted into for this instantiation
-    size_t& conf = configured[ctx->device & 63];
-    if (pl.smem > conf) {
-        VM_CUDA(cudaFuncSetAttribute(k_vp_pass<K, VAR, MODE, U, SPLIT, POW2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-        conf = pl.smem;
-    }
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(pl.grid);
-    cfg.blockDim = dim3(pl.threads);
-    cfg.dynamicSmemBytes = pl.smem;
-    cfg.stream = ctx->stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // PDL: see griddepcontrol.wait in the kernel
-    attr[0].val.programmaticStreamSerializationAllowed = ctx->no_pdl ? 0 : 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    VM_CUDA(cudaLaunchKernelEx(&cfg, k_vp_pass<K, VAR, MODE, U, SPLIT, POW2>, x, v, w, dcoef, out, P, F));
-    ++ctx->launches;
-}
-
-template <int K, int MODE>
-void launch_pass_var(vm_ctx* ctx, const DepositPlan& pl, double* x, double* v, const double* w,
-                     const double* dcoef, double* out, const PassParams& P, const FinishParams& F)
-{
-    const bool split = (MODE == MODE_PUSH_DEPOSIT) && P.kick2 != 0.0;
-    // the mask form of the periodic wrap is only specialised for the lane-private variant (small grids)
-    const bool pow2 = P.map.mask >= 0;
-#define VM_PASS_VAR(V, PW)                                                                               \
-    if (MODE == MODE_PUSH_DEPOSIT && split) launch_pass_inst<K, V, MODE, (MODE == MODE_PUSH_DEPOSIT), PW>(ctx, pl, x, v, w, dcoef, out, P, F); \
-    else launch_pass_inst<K, V, MODE, false, PW>(ctx, pl, x, v, w, dcoef, out, P, F)
-    switch (pl.var) {
-        case VAR_PRIV:
-            if (pow2) { VM_PASS_VAR(VAR_PRIV, true); } else { VM_PASS_VAR(VAR_PRIV, false); }
-            break;
-        case VAR_MATCH: VM_PASS_VAR(VAR_MATCH, false); break;
-        case VAR_XOR: VM_PASS_VAR(VAR_XOR, false); break;
-        default: VM_PASS_VAR(VAR_ATOMIC, false); break;
-    }
-#undef VM_PASS_VAR
-}
-
-template <int MODE>
-void launch_pass(vm_ctx* ctx, int order, const DepositPlan& pl, double* x, double* v, const double* w,
+void launch_pass(vm_ctx* ctx, int mode, int order, const DepositPlan& pl, double* x, double* v, const double* w,
                  const double* dcoef, double* out, const PassParams& P, const FinishParams& F)
 {
     switch (order) {
-        case 2: launch_pass_var<2, MODE>(ctx, pl, x, v, w, dcoef, out, P, F); break;
-        case 3: launch_pass_var<3, MODE>(ctx, pl, x, v, w, dcoef, out, P, F); break;
-        case 4: launch_pass_var<4, MODE>(ctx, pl, x, v, w, dcoef, out, P, F); break;
-        case 5: launch_pass_var<5, MODE>(ctx, pl, x, v, w, dcoef, out, P, F); break;
-        case 6: launch_pass_var<6, MODE>(ctx, pl, x, v, w, dcoef, out, P, F); break;
+        case 2: vm_launch_pass_k2(ctx, mode, pl, x, v, w, dcoef, out, P, F); break;
+        case 3: vm_launch_pass_k3(ctx, mode, pl, x, v, w, dcoef, out, P, F); break;
+        case 4: vm_launch_pass_k4(ctx, mode, pl, x, v, w, dcoef, out, P, F); break;
+        case 5: vm_launch_pass_k5(ctx, mode, pl, x, v, w, dcoef, out, P, F); break;
+        case 6: vm_launch_pass_k6(ctx, mode, pl, x, v, w, dcoef, out, P, F); break;
         default: throw vm_error(VM_ERR_UNSUPPORTED, "spline order must be in 2..6");
     }
 }
@@ -461,9 +254,21 @@ static void pass_with_deposit(vm_field* f, vm_particles* p, int pass_mode, int d
     vm_ctx* ctx = f->ctx;
     const int n = f->n;
     const int ncols = n;   // partial rows hold the grid only (the K/M sums live in their own rows)
-    // the 32-40 B/particle passes need more resident warps than the deposit-only pass (measured)
-    DepositPlan pl = plan_deposit(ctx, n, f->order - 1, pass_mode == MODE_PUSH_DEPOSIT ? n + f->order : 0, deposit_mode,
-                                  pass_mode == MODE_DEPOSIT ? VM_PRIV_MIN_WARPS : 12);
+    const int pmw = ctx->priv_min_warps > 0 ? ctx->priv_min_warps
+                                            : (pass_mode == MODE_DEPOSIT ? VM_PRIV_MIN_WARPS : VM_PRIV_MIN_WARPS_PUSH);
+    // fused pass on a mesh with more than 16 cells: plan with the 16-fold gather table first -- it only exists in
+    // the lane-private variant, so fall back to the plain table when the plan picks another one
+    bool repg = pass_mode == MODE_PUSH_DEPOSIT && n > 16 && !ctx->no_repg && deposit_mode != VM_DEPOSIT_ATOMIC;
+    DepositPlan pl{};
+    if (repg) {
+        try { pl = plan_deposit(ctx, n, f->order - 1, (int)vm_gather_table_doubles(n, f->order, true), deposit_mode, pmw); }
+        catch (const vm_error&) { pl.var = -1; }
+        if (pl.var != VAR_PRIV) repg = false;
+    }
+    if (!repg)
+        pl = plan_deposit(ctx, n, f->order - 1, pass_mode == MODE_PUSH_DEPOSIT ? (int)vm_gather_table_doubles(n, f->order, false) : 0,
+                          deposit_mode, pmw);
+    P.repg = repg ? 1 : 0;
     P.map = f->map;
     P.n = p->n;
     P.rep_log2 = pl.rep_log2;
@@ -493,11 +298,7 @@ static void pass_with_deposit(vm_field* f, vm_particles* p, int pass_mode, int d
     // the dominant kernel of its caller: the fused pass inside vm_vp_run, the deposit pass elsewhere
     const bool prof = (pass_mode == MODE_PUSH_DEPOSIT) || (pass_mode == MODE_DEPOSIT && prof_deposit);
     if (prof) vm_prof_mark(ctx);
-    switch (pass_mode) {
-        case MODE_DEPOSIT: launch_pass<MODE_DEPOSIT>(ctx, f->order, pl, p->x, p->v, p->w, f->dcoef, out, P, F); break;
-        case MODE_PUSH_DEPOSIT: launch_pass<MODE_PUSH_DEPOSIT>(ctx, f->order, pl, p->x, p->v, p->w, f->dcoef, out, P, F); break;
-        default: launch_pass<MODE_DRIFT_DEPOSIT>(ctx, f->order, pl, p->x, p->v, p->w, f->dcoef, out, P, F); break;
-    }
+    launch_pass(ctx, pass_mode, f->order, pl, p->x, p->v, p->w, f->dcoef, out, P, F);
     if (prof) vm_prof_mark(ctx);
     if (pl.var != VAR_ATOMIC && F.mode == FINISH_NONE) vm_field_reduce_rows(f, out, pl.grid, ncols, f->rhs);
     if (want_solve && F.mode != FINISH_REDUCE_SOLVE && F.mode != FINISH_EXCHANGE_SOLVE) vm_field_solve_local(f, true);

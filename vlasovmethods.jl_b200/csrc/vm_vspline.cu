@@ -21,34 +21,37 @@
 
 struct VCell {
     double inv_h, off;   // t = v * inv_h + off  in cell units
+    double ncell_d;      // (double)ncell
+    double slack;        // rounding slack of the affine map at the domain ends
     int ncell, k;
 };
 
+// Cell index and local coordinate of velocity v.  Always returns an in-range cell (so callers can stay
+// branch-free); the boolean says whether v lies inside [vmin, vmax] -- outside (or NaN) nothing is deposited
+// and the spline evaluates to zero.  The end points themselves may land a few ulp outside [0, ncell] after
+// the affine map, hence the slack.
 __device__ __forceinline__ bool vcell_of(const VCell& m, double v, int& c, double& xi)
 {
     double t = fma(v, m.inv_h, m.off);
-    // outside [vmin, vmax] (or NaN): no contribution.  The end points themselves may land a few ulp
-    // outside [0, ncell] after the affine map, so the test carries that rounding slack.
-    const double slack = 2e-15 * (double)m.ncell;
-    if (!(t >= -slack && t <= (double)m.ncell + slack)) return false;
-    t = fmin(fmax(t, 0.0), (double)m.ncell);
+    const bool ok = (t >= -m.slack) && (t <= m.ncell_d + m.slack);
+    t = fmin(fmax(t, 0.0), m.ncell_d);              // fmax(NaN, 0) = 0: in range for any input
     c = min(__double2int_rd(t), m.ncell - 1);
     xi = t - (double)c;
-    return true;
+    return ok;
 }
 
 // ------------------------------------------------------------ v deposit -----
 // STRAIGHT = true: interior values always computed, the rare clamped-end cells override them (best in the
 // stand-alone deposit pass); false: if/else (best inside the register-tight RK stage pass) -- A/B measured.
-template <int K, int VAR, bool STRAIGHT = true>
-__device__ __forceinline__ void vdeposit_one(double vp, double wp, bool active, const VCell& m,
-                                             const double* __restrict__ cellpoly, double* __restrict__ wg,
-                                             int npar, int rep_log2, int rep, int lane)
+// Cell and deposit weights of one particle (no shared-memory access: callers batch this for several particles
+// before the read-modify-writes, see k_vp_pass).  Returns whether the particle deposits at all.
+template <int K, bool STRAIGHT>
+__device__ __forceinline__ bool vdeposit_prepare(double vp, double wp, bool active, const VCell& m,
+                                                 const double* __restrict__ cellpoly, int& c, double (&val)[K])
 {
-    int c = 0;
     double xi = 0.0;
+    c = 0;
     active = active && vcell_of(m, vp, c, xi);
-    double val[K];
     if (!active) wp = 0.0;
     const bool interior = (c >= K - 1 && c <= m.ncell - K);
     if (STRAIGHT || interior) bspline_uniform_w<K>(xi, wp, val);   // interior cells: uniform cardinal splines (x weight)
@@ -62,6 +65,17 @@ __device__ __forceinline__ void vdeposit_one(double vp, double wp, bool active, 
             val[j] = s * wp;
         }
     }
+    return active;
+}
+
+template <int K, int VAR, bool STRAIGHT = true>
+__device__ __forceinline__ void vdeposit_one(double vp, double wp, bool active, const VCell& m,
+                                             const double* __restrict__ cellpoly, double* __restrict__ wg,
+                                             int npar, int rep_log2, int rep, int lane)
+{
+    int c;
+    double val[K];
+    active = vdeposit_prepare<K, STRAIGHT>(vp, wp, active, m, cellpoly, c, val);
     scatter<K, VAR>(wg, rep_log2, rep, lane, c, val, active);
 }
 
@@ -175,9 +189,7 @@ __device__ __forceinline__ void eval_f_df(const double* __restrict__ psh, const 
 {
     int c;
     double xi;
-    f = 0.0;
-    df = 0.0;
-    if (!vcell_of(m, v, c, xi)) return;
+    const bool ok = vcell_of(m, v, c, xi);          // branch-free: out-of-range values are zeroed by selects
     const double* q = psh + c * PolyRow<K>::stride;
     double sf = q[K - 1], sd = (double)(K - 1) * q[K - 1];
 #pragma unroll
@@ -185,8 +197,8 @@ __device__ __forceinline__ void eval_f_df(const double* __restrict__ psh, const 
         sf = fma(sf, xi, q[j]);
         if (j >= 1) sd = fma(sd, xi, (double)j * q[j]);
     }
-    f = sf;
-    df = (K > 1) ? sd * m.inv_h : 0.0;
+    f = ok ? sf : 0.0;
+    df = (ok && K > 1) ? sd * m.inv_h : 0.0;
 }
 
 // ------------------------------------------------ fused RK438 stage pass ----
@@ -209,8 +221,11 @@ struct StageParams {
     double w0;
 };
 
-template <int K, int VAR, int STAGE>
-__global__ void __launch_bounds__(1024, 1)
+// MAXT < 1024 (the lane-private replica grids of the default 41-knot basis leave room for 20 warps): the
+// register budget of the absent warps pays for a software-pipelined load of the next iteration's lines;
+// MAXT == 1024 (64 registers) only prefetches them into L2.
+template <int K, int VAR, int STAGE, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1)
 k_lb_stage(const double* v, const double* __restrict__ w, long np, VCell m, const double* __restrict__ cellpoly,
            const double* __restrict__ poly, const double* __restrict__ mom, const StageParams S, int npar, int rep_log2,
            double* __restrict__ out, const FinishParams F)
@@ -231,7 +246,10 @@ k_lb_stage(const double* v, const double* __restrict__ w, long np, VCell m, cons
     const double A1 = mom[5], A2 = mom[6];
 
     // STAGE s uses k_1 .. k_{s-1} (compile time): no pointer tests in the particle loop
-    auto one = [&](double vp, double wp, double k1, double k2, double k3, bool active, double& ks, double& qn) {
+    // phase A of a particle (reads the polynomial table only); the replica-grid read-modify-writes of the
+    // particles of an iteration follow together, so that their dependency chains overlap (see k_vp_pass)
+    auto one = [&](double vp, double wp, double k1, double k2, double k3, bool& active, double& ks, double& qn, int& cc,
+                   double (&val)[K]) {
         double q = vp;
         if (STAGE >= 2) {
             double t = S.a1 * k1;
@@ -252,7 +270,7 @@ k_lb_stage(const double* v, const double* __restrict__ w, long np, VCell m, cons
             t = S.cs * ks;
         }
         qn = fma(S.dt, t, vp);
-        vdeposit_one<K, VAR, false>(qn, wp, active, m, cellpoly, wg, npar, rep_log2, rep, lane);
+        active = vdeposit_prepare<K, false>(qn, wp, active, m, cellpoly, cc, val);
     };
 
     const unsigned npairs = (unsigned)(np >> 1);
@@ -260,40 +278,59 @@ k_lb_stage(const double* v, const double* __restrict__ w, long np, VCell m, cons
     const unsigned gtid = blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned iters = (npairs + stride - 1) / stride;    // uniform trip count (warp-collective scatter variants)
     unsigned q = gtid;
+    constexpr bool PIPE = (MAXT < 1024);
+    struct Lines { double2 vv, ww, a, b, c; };
+    auto load = [&](Lines& L, unsigned qq) {
+        L.vv = L.ww = L.a = L.b = L.c = make_double2(0., 0.);
+        if (qq < npairs) {
+            L.vv = ld_stream2(v + 2 * (size_t)qq);
+            L.ww = S.uw ? make_double2(S.w0, S.w0) : ld_stream2(w + 2 * (size_t)qq);
+            if (STAGE >= 2) L.a = ld_stream2(S.k1 + 2 * (size_t)qq);
+            if (STAGE >= 3) L.b = ld_stream2(S.k2 + 2 * (size_t)qq);
+            if (STAGE >= 4) L.c = ld_stream2(S.k3 + 2 * (size_t)qq);
+        }
+    };
+    Lines cur, nxt;
+    if (PIPE) load(cur, q);
     for (unsigned it = 0; it < iters; ++it, q += stride) {
         const bool active = q < npairs;
-        // the pass has no registers left for software-pipelined loads: pull the next iteration's lines into L2
-        // (one lane per 128-byte line = 8 pairs)
-        if ((lane & 7) == 0 && q + stride < npairs) {
-            const size_t e = 2 * (size_t)(q + stride);
+        // pull the lines of a later iteration into L2 (one lane per 128-byte line = 8 pairs): the next one when the
+        // pass has no registers for software-pipelined loads, the one after next otherwise
+        const unsigned qp = q + (PIPE ? 2 : 1) * stride;
+        if ((lane & 7) == 0 && qp < npairs) {
+            const size_t e = 2 * (size_t)qp;
             prefetch_l2(v + e);
             if (!S.uw) prefetch_l2(w + e);
             if (STAGE >= 2) prefetch_l2(S.k1 + e);
             if (STAGE >= 3) prefetch_l2(S.k2 + e);
             if (STAGE >= 4) prefetch_l2(S.k3 + e);
         }
-        double2 vv = make_double2(0., 0.), ww = vv, a = vv, b = vv, c = vv;
-        if (active) {
-            vv = ld_stream2(v + 2 * (size_t)q);
-            ww = S.uw ? make_double2(S.w0, S.w0) : ld_stream2(w + 2 * (size_t)q);
-            if (STAGE >= 2) a = ld_stream2(S.k1 + 2 * (size_t)q);
-            if (STAGE >= 3) b = ld_stream2(S.k2 + 2 * (size_t)q);
-            if (STAGE >= 4) c = ld_stream2(S.k3 + 2 * (size_t)q);
-        }
+        if (PIPE) load(nxt, q + stride);
+        else load(cur, q);
         double2 ks, qn;
-        one(vv.x, ww.x, a.x, b.x, c.x, active, ks.x, qn.x);
-        one(vv.y, ww.y, a.y, b.y, c.y, active, ks.y, qn.y);
+        int c0, c1;
+        double val0[K], val1[K];
+        bool act0 = active, act1 = active;
+        one(cur.vv.x, cur.ww.x, cur.a.x, cur.b.x, cur.c.x, act0, ks.x, qn.x, c0, val0);
+        one(cur.vv.y, cur.ww.y, cur.a.y, cur.b.y, cur.c.y, act1, ks.y, qn.y, c1, val1);
+        scatter<K, VAR>(wg, rep_log2, rep, lane, c0, val0, act0);
+        scatter<K, VAR>(wg, rep_log2, rep, lane, c1, val1, act1);
         if (active) {
             if (STAGE < 4) st_stream2(S.kout + 2 * (size_t)q, ks);
             if (S.qout) st_stream2(S.qout + 2 * (size_t)q, qn);
         }
+        if (PIPE) cur = nxt;
     }
     if ((np & 1) && blockIdx.x == 0 && warp == 0) {
         const bool active = (lane == 0);
         const long p = np - 1;
         double ks = 0., qn = 0.;
+        int c0;
+        double val0[K];
+        bool act0 = active;
         one(active ? v[p] : 0.0, active ? (S.uw ? S.w0 : w[p]) : 0.0, (active && STAGE >= 2) ? S.k1[p] : 0.0,
-            (active && STAGE >= 3) ? S.k2[p] : 0.0, (active && STAGE >= 4) ? S.k3[p] : 0.0, active, ks, qn);
+            (active && STAGE >= 3) ? S.k2[p] : 0.0, (active && STAGE >= 4) ? S.k3[p] : 0.0, act0, ks, qn, c0, val0);
+        scatter<K, VAR>(wg, rep_log2, rep, lane, c0, val0, act0);
         if (active) {
             if (STAGE < 4) S.kout[p] = ks;
             if (S.qout) S.qout[p] = qn;
@@ -547,6 +584,8 @@ VCell vcell(const vm_vspline* s)
     m.inv_h = (double)((long double)s->ncell / ((long double)s->b - (long double)s->a));
     m.off = -s->a * m.inv_h;
     m.ncell = s->ncell;
+    m.ncell_d = (double)s->ncell;
+    m.slack = 2e-15 * (double)s->ncell;
     m.k = s->order;
     return m;
 }
@@ -648,17 +687,17 @@ void project_dev(vm_vspline* s, const double* v, const double* w, long np)
     after_deposit(s, d);
 }
 
-template <int K, int VAR, int STAGE>
+template <int K, int VAR, int STAGE, int MAXT>
 void launch_stage_inst(vm_vspline* s, const VDepSetup& d, const double* v, const double* w, long np, const StageParams& S)
 {
     vm_ctx* ctx = s->ctx;
     static size_t configured[64] = {};
     size_t& conf = configured[ctx->device & 63];
     if (d.pl.smem > conf) {
-        VM_CUDA(cudaFuncSetAttribute(k_lb_stage<K, VAR, STAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d.pl.smem));
+        VM_CUDA(cudaFuncSetAttribute(k_lb_stage<K, VAR, STAGE, MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d.pl.smem));
         conf = d.pl.smem;
     }
-    k_lb_stage<K, VAR, STAGE><<<d.pl.grid, d.pl.threads, d.pl.smem, ctx->stream>>>(
+    k_lb_stage<K, VAR, STAGE, MAXT><<<d.pl.grid, d.pl.threads, d.pl.smem, ctx->stream>>>(
         v, w, np, vcell(s), s->cellpoly, s->poly, s->moments, S, s->npar, d.pl.rep_log2, d.out, d.F);
     VM_LAUNCHED(ctx);
 }
@@ -667,8 +706,11 @@ void launch_stage_inst(vm_vspline* s, const VDepSetup& d, const double* v, const
 template <int K, int STAGE>
 void launch_stage_var(vm_vspline* s, const VDepSetup& d, const double* v, const double* w, long np, const StageParams& S)
 {
-    if (d.pl.var == VAR_PRIV) launch_stage_inst<K, VAR_PRIV, STAGE>(s, d, v, w, np, S);
-    else launch_stage_inst<K, VAR_MATCH, STAGE>(s, d, v, w, np, S);
+    const bool pipe = d.pl.threads <= 640 && s->ctx->pairs != 1;      // pairs == 1: A/B switch back to the L2-prefetch-only loop
+    if (d.pl.var == VAR_PRIV) {
+        if (pipe) launch_stage_inst<K, VAR_PRIV, STAGE, 640>(s, d, v, w, np, S);
+        else launch_stage_inst<K, VAR_PRIV, STAGE, 1024>(s, d, v, w, np, S);
+    } else launch_stage_inst<K, VAR_MATCH, STAGE, 1024>(s, d, v, w, np, S);
 }
 
 template <int K>
