@@ -341,8 +341,10 @@ def run_gpu(args):
                "particles_per_s": nloc * world / dep_ms * 1e3,
                "per_particle_weights": {"ms": dep_ms_gw, "algorithmic_bytes_per_particle": 16,
                                         "GBps": 16 * nloc / dep_ms_gw / 1e6, "frac": 16 * nloc / dep_ms_gw / 1e6 / peak},
-               "note": "with the uniform weight of this workload the pass reads 8 B/particle and is issue-bound; "
-                       "with per-particle weights (16 B/particle) it runs at the HBM roofline fraction given above",
+               "note": "with the uniform weight of this workload the pass reads 8 B/particle and is bound by the L1TEX/"
+                       "shared-memory data pipe, not by HBM: 16 wavefronts per warp of particles for the K=4 read-modify-"
+                       "writes of the lane-private replicas + 2 for the loads = 93 % of the LSU wavefront peak (ncu, "
+                       "profiles/README.md); with per-particle weights (16 B/particle) see per_particle_weights",
                "shared_atomics": 0, "mode": "deterministic (lane-private replicas)"}
     secondary = None
     if not args.no_secondary:
@@ -351,7 +353,18 @@ def run_gpu(args):
         lb = timed(lambda: vs.lb_rhs(p, 1.0, False, to_host=False), 5)
         clb = timed(lambda: vs.lb_rhs(p, 1.0, True, to_host=False), 5)
         rk = timed(lambda: vs.rk438_run(p, 1e-3, 5, 1.0, True, 0), 2) / 5
+        # mesh-size sweep of the fused step (BASELINE configs[4]: 64-1024 spline modes), same particles, cubic
+        p.fill(vm._lib.VM_FILL_BUMP_ON_TAIL, [EPS, KAPPA, ALPHA, SIGMA, V0], SEED, lo, ntot)
+        mesh = {}
+        for nh in (32, 64, 128, 256, 1024):
+            f2 = vm.DeviceField(ctx, 0.0, L_DOMAIN, ORDER, nh, 0)
+            f2.run(p, DT, 3, 0, flags, 1.0)
+            t = timed(lambda: f2.run(p, DT, 10, 0, flags, 1.0), 2) / 10
+            mesh[str(nh)] = {"ms_per_step": t, "particle_steps_per_s": ntot / t * 1e3,
+                             "step_hbm_frac": ALG_BYTES_PER_PARTICLE * nloc / t / 1e6 / peak}
+            f2.close()
         secondary = {"particles_total": ntot, "vspline": "41 knots, order 4, Dirichlet, v in (-10,10)",
+                     "mesh_sweep_n_basis": mesh,
                      "weights": "uniform w = 1/N: not streamed (8 B less per deposit pass)",
                      "lb_rhs_evals_per_s": ntot / lb * 1e3, "lb_rhs_hbm_frac": 24 * nloc / lb / 1e6 / peak,
                      "clb_rhs_evals_per_s": ntot / clb * 1e3, "clb_rhs_hbm_frac": 32 * nloc / clb / 1e6 / peak,

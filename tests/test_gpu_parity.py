@@ -113,7 +113,7 @@ def test_deposit_all_replica_variants(vm, oracle, rng, replicas):
     assert relmax(fld.rhs, ref) <= RTOL
     fld.close(); p.close(); c.close()
 
-@pytest.mark.parametrize("n,k", [(24, 4), (32, 4), (64, 4), (100, 4), (128, 4), (64, 3), (40, 5), (128, 6), (64, 2)])
+@pytest.mark.parametrize("n,k", [(24, 4), (32, 4), (64, 4), (100, 4), (128, 4), (64, 3), (40, 5), (128, 6), (64, 2), (200, 4)])
 @pytest.mark.parametrize("tune", [{}, {"pairs": 1, "no_repg": 1, "priv_min_warps": 12}, {"pairs": 4}, {"pairs": 8, "no_repg": 1}],
                          ids=["auto", "round1", "pairs4", "pairs8-plain-table"])
 def test_pipeline_depths_match_oracle(vm, oracle, rng, n, k, tune):
@@ -126,7 +126,7 @@ def test_pipeline_depths_match_oracle(vm, oracle, rng, n, k, tune):
         c.set_tuning(key, val)
     kappa = 0.3
     a, b = 0.0, 2 * math.pi / kappa
-    npart = 1_200_001
+    npart = 700_001
     x = rng.uniform(a, b, npart); v = rng.standard_normal(npart)
     fld = vm.DeviceField(c, a, b, k, n, 0)
     p = vm.DeviceParticles(c, npart)
@@ -547,3 +547,24 @@ def test_error_reporting(vm, ctx):
     f = vm.DeviceField(c2, 0.0, 1.0, 4, 16, 0)
     with pytest.raises(vm.VMError):
         f.deposit(vm.DeviceParticles(ctx, 4), 0)       # different contexts
+
+
+def test_interpreter_exit_without_close(tmp_path):
+    """A script that never calls close() must exit cleanly: shutdown finalises the wrappers in no particular
+    order, and a child handle destroyed after its context used to be a use-after-free (segfault at exit)."""
+    import subprocess
+    import sys
+    from pathlib import Path
+    root = Path(__file__).resolve().parent.parent
+    script = tmp_path / "noclose.py"
+    script.write_text(
+        "import sys; sys.path.insert(0, %r)\n"
+        "from __graft_entry__ import load_package\n"
+        "vm = load_package()\n"
+        "ctx = vm.Context(0)\n"
+        "p = vm.DeviceParticles(ctx, 1000); f = vm.DeviceField(ctx, 0.0, 1.0, 4, 16, 0)\n"
+        "vs = vm.DeviceVSpline(ctx, -10.0, 10.0, 41, 4, 1)\n"
+        "p.fill(vm._lib.VM_FILL_UNIFORM, [0.0, 1.0, -1.0, 1.0], 1); f.run(p, 0.1, 2, 0, 0, 1.0)\n"
+        "print('done')\n" % str(root))
+    r = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "done" in r.stdout, (r.returncode, r.stderr[-2000:])

@@ -5,12 +5,29 @@ opaque handles and convert numpy arrays at the boundary.
 """
 from __future__ import annotations
 
+import atexit
 import ctypes as C
 import weakref
 
 import numpy as np
 
 from . import _lib as L
+
+
+_live_contexts = weakref.WeakSet()
+
+
+def _close_all_contexts():
+    """Interpreter shutdown finalises objects in no particular order; a child handle destroyed after its context
+    is a use-after-free inside the library.  Close every context (children first) while the world is intact."""
+    for c in list(_live_contexts):
+        try:
+            c.close()
+        except Exception:
+            pass
+
+
+atexit.register(_close_all_contexts)
 
 
 def _f64(a, shape=None):
@@ -28,6 +45,7 @@ class Context:
         self._children = weakref.WeakSet()      # particles / fields / splines created on this context
         L.check(L.lib().vm_ctx_create(int(device), C.byref(self._h)))
         self.device = int(device)
+        _live_contexts.add(self)
 
     # -- lifetime ---------------------------------------------------------
     def close(self):
@@ -150,7 +168,9 @@ class DeviceParticles:
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:
-            L.lib().vm_particles_destroy(self._h)
+            if self.ctx._h.value:                # after its context: destroying would dereference the freed context (only
+                                                 # reachable in interpreter shutdown; the leak ends with the process)
+                L.lib().vm_particles_destroy(self._h)
             self._h = C.c_void_p()
 
     def __del__(self):
@@ -216,7 +236,9 @@ class DeviceField:
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:
-            L.lib().vm_field_destroy(self._h)
+            if self.ctx._h.value:                # after its context: destroying would dereference the freed context (only
+                                                 # reachable in interpreter shutdown; the leak ends with the process)
+                L.lib().vm_field_destroy(self._h)
             self._h = C.c_void_p()
 
     def __del__(self):
@@ -314,7 +336,9 @@ class DeviceVSpline:
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:
-            L.lib().vm_vspline_destroy(self._h)
+            if self.ctx._h.value:                # after its context: destroying would dereference the freed context (only
+                                                 # reachable in interpreter shutdown; the leak ends with the process)
+                L.lib().vm_vspline_destroy(self._h)
             self._h = C.c_void_p()
 
     def __del__(self):

@@ -370,7 +370,9 @@ inline DepositPlan plan_deposit(vm_ctx* ctx, int n_real, int ghost, int extra_do
 
     if (mode != VM_DEPOSIT_ATOMIC && !tuned) {
         // next best (measured): 16 or 8 replicas per warp with xor-shuffle collision handling, provided
-        // at least 24 warps stay resident; below that MATCH.ANY grouping with 32 warps wins again
+        // at least 24 warps stay resident; below that MATCH.ANY grouping with 32 warps wins again.  (Running the
+        // xor variant with 6 warps and the deep software pipeline of the lane-private variant, or with 4 replicas,
+        // measured 2-4x slower at n_h = 200 .. 1024: its shuffles and warp syncs serialise within a warp.)
         for (int rl = 4; rl >= 3; --rl) {
             const size_t per_warp = ((size_t)n << rl) * sizeof(double);
             const size_t b1 = budget_of(1);

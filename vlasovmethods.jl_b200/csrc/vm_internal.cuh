@@ -260,11 +260,19 @@ __device__ __forceinline__ int wrap_add(int i, int j, int n)
     return r >= n ? r - n : r;
 }
 
-// streaming 16-byte loads/stores (read once / written once per pass)
+// streaming 16-byte loads/stores (read once / written once per pass).  Loads do not allocate in L1
+// (LDG.E.NA): the replica grids of mid-size meshes take up to 227 KB of the 256 KB L1/shared array, and what is
+// left should not be churned by data that is never re-read.  Measured against the evict-first form
+// (ld.global.cs, -DVM_LD_CS): -4 % at n_h = 32, -3 % at n_h = 64, equal at n_h = 16 / 128 and in the v-space passes.
+#ifdef VM_LD_CS
+#define VM_LD_STREAM "ld.global.cs"
+#else
+#define VM_LD_STREAM "ld.global.L1::no_allocate"
+#endif
 __device__ __forceinline__ double2 ld_stream2(const double* p)
 {
     double2 r;
-    asm volatile("ld.global.cs.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+    asm volatile(VM_LD_STREAM ".v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
     return r;
 }
 __device__ __forceinline__ void st_stream2(double* p, double2 v)
@@ -274,7 +282,7 @@ __device__ __forceinline__ void st_stream2(double* p, double2 v)
 __device__ __forceinline__ double ld_stream(const double* p)
 {
     double r;
-    asm volatile("ld.global.cs.f64 %0, [%1];" : "=d"(r) : "l"(p));
+    asm volatile(VM_LD_STREAM ".f64 %0, [%1];" : "=d"(r) : "l"(p));
     return r;
 }
 __device__ __forceinline__ void st_stream(double* p, double v)

@@ -32,6 +32,7 @@ struct PassParams {
 // (ncu, n_h = 32: 25 % of all shared-memory wavefronts of the fused pass were such conflicts, and the pass is
 // co-limited by the shared-memory data pipe); with one copy per bank pair every gather is conflict-free.
 #define VM_GATHER_COPIES 16
+#define VM_GATHER_TABLE_MAX_BYTES (45 * 1024)   // beyond this the copies cost more replica-grid warps than they save
 template <int K, bool REPG = false>
 __device__ __forceinline__ double gather_dphi(const double* __restrict__ dsh, int b0, double xi)
 {
@@ -283,7 +284,7 @@ void launch_pass_inst(vm_ctx* ctx, const DepositPlan& pl, double* x, double* v, 
             return launch_pass_depth<K, VAR, MODE, SPLIT, POW2, 1, 1024, true>(ctx, pl, x, v, w, dcoef, out, P, F);
         }
     }
-    if (P.repg) throw vm_error(VM_ERR_UNSUPPORTED, "internal: replicated gather table without the lane-private fused pass");
+    if (P.repg) throw vm_error(VM_ERR_UNSUPPORTED, "internal: replicated gather table requested for a deposit variant without it");
     launch_pass_depth<K, VAR, MODE, SPLIT, POW2, U0, 1024, false>(ctx, pl, x, v, w, dcoef, out, P, F);
 }
 

@@ -258,7 +258,8 @@ static void pass_with_deposit(vm_field* f, vm_particles* p, int pass_mode, int d
                                             : (pass_mode == MODE_DEPOSIT ? VM_PRIV_MIN_WARPS : VM_PRIV_MIN_WARPS_PUSH);
     // fused pass on a mesh with more than 16 cells: plan with the 16-fold gather table first -- it only exists in
     // the lane-private variant, so fall back to the plain table when the plan picks another one
-    bool repg = pass_mode == MODE_PUSH_DEPOSIT && n > 16 && !ctx->no_repg && deposit_mode != VM_DEPOSIT_ATOMIC;
+    bool repg = pass_mode == MODE_PUSH_DEPOSIT && n > 16 && !ctx->no_repg && deposit_mode != VM_DEPOSIT_ATOMIC &&
+                vm_gather_table_doubles(n, f->order, true) * sizeof(double) <= VM_GATHER_TABLE_MAX_BYTES;
     DepositPlan pl{};
     if (repg) {
         try { pl = plan_deposit(ctx, n, f->order - 1, (int)vm_gather_table_doubles(n, f->order, true), deposit_mode, pmw); }
