@@ -32,11 +32,12 @@ struct VCell {
 // the affine map, hence the slack.
 __device__ __forceinline__ bool vcell_of(const VCell& m, double v, int& c, double& xi)
 {
-    double t = fma(v, m.inv_h, m.off);
-    const bool ok = (t >= -m.slack) && (t <= m.ncell_d + m.slack);
-    t = fmin(fmax(t, 0.0), m.ncell_d);              // fmax(NaN, 0) = 0: in range for any input
-    c = min(__double2int_rd(t), m.ncell - 1);
-    xi = t - (double)c;
+    const double t = fma(v, m.inv_h, m.off);
+    const bool ok = (t >= -m.slack) && (t <= m.ncell_d + m.slack);      // false for NaN
+    // the conversion saturates and maps NaN to 0, so the integer clamp alone keeps c in range (the fp64
+    // fmin/fmax clamp of t it replaces cost ~15 instructions of selects and moves per lookup)
+    c = max(0, min(__double2int_rd(t), m.ncell - 1));
+    xi = ok ? t - (double)c : 0.0;                                      // end points: xi within a few ulp of [0, 1]
     return ok;
 }
 
