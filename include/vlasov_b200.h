@@ -165,6 +165,22 @@ typedef enum vm_deposit_mode {
 /* projection!(potential, dist): src/projections/potential.jl:2-22.
  * rhs_i = sum_p w_p B_i(x_p) over this rank's particles (local partial). */
 int vm_deposit(vm_field* f, vm_particles* p, int mode);
+
+/* Introspection (no reference counterpart; no device needed): the launch plan the library would choose for a
+ * particle pass over a periodic mesh of n_basis cells on a device with sm_count SMs and smem_optin_bytes of
+ * opt-in shared memory per CTA (B200: 148, 232448).  pass: 0 = deposit only (vm_deposit), 1 = fused
+ * kick+drift+deposit step (vm_vp_run), 2 = drift+deposit prologue. */
+typedef struct vm_pass_plan {
+    int variant;        /* 0 lane-private replicas, 1 MATCH.ANY grouping, 2 shared atomics, 3 xor-shuffle */
+    int replicas;       /* replica grids per warp (per CTA for variant 2) */
+    int grid, threads;  /* CTAs, threads per CTA */
+    int pairs;          /* pairs of particles in flight per thread */
+    int max_threads;    /* launch bound of the kernel instantiation (registers per thread = 65536 / max_threads) */
+    int gather_copies;  /* copies of the field table in shared memory (16: bank-conflict-free gather) */
+    size_t smem_bytes;  /* dynamic shared memory per CTA */
+} vm_pass_plan;
+int vm_pass_plan_query(int sm_count, size_t smem_optin_bytes, int n_basis, int order, int pass, int deposit_mode,
+                       vm_pass_plan* out);
 /* PoissonSolvers.update!(potential) (src/models/vlasov_poisson.jl:14),
  * update!(::PoissonField, x, w, t) (src/electric_field.jl:45): all-reduce rhs over
  * the ranks, then solve S phi = rhs - mean(rhs), sum(phi) = 0. */

@@ -102,3 +102,64 @@ def test_sharded_step_world2_gloo(tmp_path):
                        capture_output=True, text=True, env=env, timeout=280)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert r.stdout.count("ok") == 2
+
+
+# ------------------------------------------------------------ launch plans (pure host logic, no GPU) ---
+B200_SMS, B200_SMEM_OPTIN = 148, 232448
+
+
+@pytest.mark.parametrize("order", [2, 3, 4, 5, 6])
+def test_pass_plans_fit_the_device_for_every_mesh_size(vm, order):
+    """vm_pass_plan_query over every mesh size the ABI accepts: the plan fits in shared memory, the CTA fits the
+    launch bound of the kernel tier that runs it, the register budget of that bound covers the pipeline depth, and
+    the replica grids + gather table are fully accounted for in the dynamic shared memory."""
+    L = vm._lib
+    sizes = list(range(1, 300)) + list(range(300, 4097, 37)) + [512, 1024, 2048, 4096]
+    for n in sizes:
+        for pass_ in (0, 1, 2):
+            p = L.pass_plan(n, order, pass_)
+            what = (n, order, pass_, p.variant, p.replicas, p.grid, p.threads, p.pairs, p.max_threads, p.gather_copies, p.smem_bytes)
+            assert p.smem_bytes <= B200_SMEM_OPTIN, what
+            ctas = p.grid // B200_SMS
+            assert p.grid == ctas * B200_SMS and ctas in (1, 2), what          # whole waves of the SM count
+            assert ctas * (p.smem_bytes + 1024) <= 227 * 1024 + 1024, what     # all CTAs of an SM resident together
+            assert p.threads % 32 == 0 and 32 <= p.threads <= p.max_threads <= 1024, what
+            assert ctas * p.threads <= 1024, what
+            assert p.pairs in (1, 2, 4, 8), what
+            regs = min(255, 65536 // max(p.max_threads, ctas * p.threads))       # what the launch bound lets ptxas use
+            assert regs >= {1: 64, 2: 64, 4: 128, 8: 255}[p.pairs], what
+            warps = p.threads // 32
+            rows = n + order - 1
+            grids = rows * p.replicas * 8 * (1 if p.variant == 2 else warps)
+            table = (n + order) * 8 * p.gather_copies if pass_ == 1 else 0
+            assert p.smem_bytes >= grids + table + p.threads * 8, what
+            if p.variant == 0:
+                assert p.replicas == 32 and warps >= 6, what
+            if p.variant == 3:
+                assert p.replicas in (8, 16) and warps >= 24, what
+            if p.gather_copies != 1:          # the 16-fold table exists only in the lane-private fused pass
+                assert p.gather_copies == 16 and pass_ == 1 and p.variant == 0 and n > 16, what
+            elif pass_ == 1 and p.variant == 0 and n > 16:   # ... and is only given up when it would cost the variant
+                assert rows * 256 * 6 + (n + order) * 128 + 6 * 256 > 227 * 1024 - 1024, what
+            if p.variant != 0:
+                assert p.pairs == (2 if pass_ == 0 else 1) and p.max_threads == 1024, what
+
+
+def test_pass_plans_of_the_benchmarked_meshes(vm):
+    """The configurations measured in profiles/README.md section 6 (cubic splines, B200)."""
+    L = vm._lib
+    p = L.pass_plan(16, 4, 1)
+    assert (p.variant, p.grid, p.threads, p.pairs, p.gather_copies) == (0, 296, 512, 1, 1)
+    p = L.pass_plan(32, 4, 1)
+    assert (p.variant, p.grid, p.threads, p.pairs, p.gather_copies) == (0, 148, 768, 1, 16)
+    p = L.pass_plan(64, 4, 1)
+    assert (p.variant, p.grid, p.threads, p.pairs, p.max_threads, p.gather_copies) == (0, 148, 384, 4, 448, 16)
+    p = L.pass_plan(128, 4, 1)
+    assert (p.variant, p.grid, p.threads, p.pairs, p.max_threads, p.gather_copies) == (0, 148, 192, 8, 192, 16)
+    p = L.pass_plan(128, 4, 0)
+    assert (p.variant, p.threads, p.pairs, p.max_threads) == (0, 192, 8, 256)
+    assert L.pass_plan(256, 4, 1).variant == 1 and L.pass_plan(1024, 4, 1).variant == 1
+    assert L.pass_plan(16, 4, 0, 1).variant == 2          # VM_DEPOSIT_ATOMIC: the warp-aggregated A/B variant
+    for bad in ((0, 4, 1), (16, 7, 1), (16, 4, 3), (5000, 4, 1)):
+        with pytest.raises(vm.VMError):
+            L.pass_plan(*bad)

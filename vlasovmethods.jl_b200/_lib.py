@@ -58,6 +58,7 @@ SIGNATURES = {
     "vm_field_get_coefficients": (_i, [_vp, _dp]),
     "vm_field_set_coefficients": (_i, [_vp, _dp]),
     "vm_field_get_stencils": (_i, [_vp, _dp, _dp]),
+    "vm_pass_plan_query": (_i, [_i, C.c_size_t, _i, _i, _i, _i, _vp]),
     "vm_deposit": (_i, [_vp, _vp, _i]),
     "vm_field_solve": (_i, [_vp]),
     "vm_field_energy": (_i, [_vp, C.POINTER(_d)]),
@@ -95,6 +96,21 @@ class VMError(RuntimeError):
     def __init__(self, code: int, msg: str):
         super().__init__(f"libvlasov_b200 error {code}: {msg}")
         self.code = code
+
+
+class PassPlan(C.Structure):
+    """vm_pass_plan (include/vlasov_b200.h)."""
+    _fields_ = [("variant", _i), ("replicas", _i), ("grid", _i), ("threads", _i), ("pairs", _i), ("max_threads", _i),
+                ("gather_copies", _i), ("smem_bytes", C.c_size_t)]
+
+
+def pass_plan(n_basis: int, order: int, pass_: int, deposit_mode: int = 0, sm_count: int = 148,
+              smem_optin_bytes: int = 232448) -> PassPlan:
+    """Launch plan for a particle pass (pure host logic: works without a GPU)."""
+    out = PassPlan()
+    check(lib().vm_pass_plan_query(int(sm_count), C.c_size_t(int(smem_optin_bytes)), int(n_basis), int(order), int(pass_),
+                                   int(deposit_mode), C.byref(out)))
+    return out
 
 
 def build() -> Path:

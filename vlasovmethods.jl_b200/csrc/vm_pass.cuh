@@ -237,6 +237,31 @@ k_vp_pass(double* __restrict__ x, double* __restrict__ v, const double* __restri
 }
 
 // ================================================================ host ======
+// Plan of one particle pass: deposit variant + CTA shape, and whether the fused pass stores its gather table
+// VM_GATHER_COPIES times.  The replicated table only exists in the lane-private variant: plan with it first and
+// fall back to the plain table when the plan picks another variant (or nothing fits).
+struct PassPlan {
+    DepositPlan pl;
+    bool repg;
+};
+inline PassPlan plan_pass(vm_ctx* ctx, int n, int order, int pass_mode, int deposit_mode)
+{
+    const int pmw = ctx->priv_min_warps > 0 ? ctx->priv_min_warps
+                                            : (pass_mode == MODE_DEPOSIT ? VM_PRIV_MIN_WARPS : VM_PRIV_MIN_WARPS_PUSH);
+    PassPlan pp{};
+    pp.repg = pass_mode == MODE_PUSH_DEPOSIT && n > 16 && !ctx->no_repg && deposit_mode != VM_DEPOSIT_ATOMIC &&
+              vm_gather_table_doubles(n, order, true) * sizeof(double) <= VM_GATHER_TABLE_MAX_BYTES;
+    if (pp.repg) {
+        try { pp.pl = plan_deposit(ctx, n, order - 1, (int)vm_gather_table_doubles(n, order, true), deposit_mode, pmw); }
+        catch (const vm_error&) { pp.pl.var = -1; }
+        if (pp.pl.var != VAR_PRIV) pp.repg = false;
+    }
+    if (!pp.repg)
+        pp.pl = plan_deposit(ctx, n, order - 1, pass_mode == MODE_PUSH_DEPOSIT ? (int)vm_gather_table_doubles(n, order, false) : 0,
+                             deposit_mode, pmw);
+    return pp;
+}
+
 template <int K, int VAR, int MODE, bool SPLIT, bool POW2, int U, int MAXT, bool REPG>
 void launch_pass_depth(vm_ctx* ctx, const DepositPlan& pl, double* x, double* v, const double* w,
                        const double* dcoef, double* out, const PassParams& P, const FinishParams& F)
@@ -261,26 +286,44 @@ void launch_pass_depth(vm_ctx* ctx, const DepositPlan& pl, double* x, double* v,
     ++ctx->launches;
 }
 
-// Pairs in flight per thread.  Full CTAs (1024 threads per SM, 64 registers each) run the shallow loop; the
-// lane-private variant with fewer warps trades its spare registers for depth (vm_auto_pairs; `pairs` tuning
-// key: A/B override).  P.repg (lane-private fused pass on meshes with more than 16 cells): replicated gather table.
+// Pairs in flight per thread and the launch bound of the instantiation that runs them.  Full CTAs (1024 threads
+// per SM, 64 registers each) run the shallow loop; the lane-private variant with fewer warps trades its spare
+// registers for depth (vm_auto_pairs; `pairs` tuning key: A/B override, rounded down to a tier the CTA fits).
+struct PassTier { int pairs, max_threads; };
+inline PassTier vm_pass_tier(int mode, int var, int per_sm, int pairs_req)
+{
+    const PassTier base{mode == MODE_DEPOSIT ? 2 : 1, 1024};
+    if (var != VAR_PRIV) return base;
+    const int u = pairs_req > 0 ? pairs_req : vm_auto_pairs(mode == MODE_DEPOSIT, per_sm);
+    if (mode == MODE_DEPOSIT) {
+        if (u >= 8 && per_sm <= 256) return PassTier{8, 256};
+        if (u >= 4 && per_sm <= 512) return PassTier{4, 512};
+    } else {
+        if (u >= 8 && per_sm <= 192) return PassTier{8, 192};
+        if (u >= 4 && per_sm <= 448) return PassTier{4, 448};
+    }
+    return base;
+}
+
+// P.repg (lane-private fused pass on meshes with more than 16 cells): replicated gather table.
 template <int K, int VAR, int MODE, bool SPLIT, bool POW2>
 void launch_pass_inst(vm_ctx* ctx, const DepositPlan& pl, double* x, double* v, const double* w,
                       const double* dcoef, double* out, const PassParams& P, const FinishParams& F)
 {
     constexpr int U0 = (MODE == MODE_DEPOSIT) ? 2 : 1;
     const int per_sm = pl.threads * (pl.grid / ctx->sm_count);      // resident threads per SM
+    const PassTier t = vm_pass_tier(MODE, VAR, per_sm, ctx->pairs);
+    if (pl.threads > t.max_threads) throw vm_error(VM_ERR_UNSUPPORTED, "internal: CTA larger than the launch bound of its tier");
     if constexpr (VAR == VAR_PRIV) {
-        const int u = ctx->pairs > 0 ? ctx->pairs : vm_auto_pairs(MODE == MODE_DEPOSIT, per_sm);
         if constexpr (MODE == MODE_DEPOSIT) {
-            if (u >= 8 && per_sm <= 256) return launch_pass_depth<K, VAR, MODE, SPLIT, POW2, 8, 256, false>(ctx, pl, x, v, w, dcoef, out, P, F);
-            if (u >= 4 && per_sm <= 512) return launch_pass_depth<K, VAR, MODE, SPLIT, POW2, 4, 512, false>(ctx, pl, x, v, w, dcoef, out, P, F);
+            if (t.pairs == 8) return launch_pass_depth<K, VAR, MODE, SPLIT, POW2, 8, 256, false>(ctx, pl, x, v, w, dcoef, out, P, F);
+            if (t.pairs == 4) return launch_pass_depth<K, VAR, MODE, SPLIT, POW2, 4, 512, false>(ctx, pl, x, v, w, dcoef, out, P, F);
         } else if constexpr (MODE == MODE_DRIFT_DEPOSIT) {
-            if (u >= 8 && per_sm <= 192) return launch_pass_depth<K, VAR, MODE, SPLIT, POW2, 8, 192, false>(ctx, pl, x, v, w, dcoef, out, P, F);
-            if (u >= 4 && per_sm <= 448) return launch_pass_depth<K, VAR, MODE, SPLIT, POW2, 4, 448, false>(ctx, pl, x, v, w, dcoef, out, P, F);
+            if (t.pairs == 8) return launch_pass_depth<K, VAR, MODE, SPLIT, POW2, 8, 192, false>(ctx, pl, x, v, w, dcoef, out, P, F);
+            if (t.pairs == 4) return launch_pass_depth<K, VAR, MODE, SPLIT, POW2, 4, 448, false>(ctx, pl, x, v, w, dcoef, out, P, F);
         } else if (P.repg) {
-            if (u >= 8 && per_sm <= 192) return launch_pass_depth<K, VAR, MODE, SPLIT, POW2, 8, 192, true>(ctx, pl, x, v, w, dcoef, out, P, F);
-            if (u >= 4 && per_sm <= 448) return launch_pass_depth<K, VAR, MODE, SPLIT, POW2, 4, 448, true>(ctx, pl, x, v, w, dcoef, out, P, F);
+            if (t.pairs == 8) return launch_pass_depth<K, VAR, MODE, SPLIT, POW2, 8, 192, true>(ctx, pl, x, v, w, dcoef, out, P, F);
+            if (t.pairs == 4) return launch_pass_depth<K, VAR, MODE, SPLIT, POW2, 4, 448, true>(ctx, pl, x, v, w, dcoef, out, P, F);
             return launch_pass_depth<K, VAR, MODE, SPLIT, POW2, 1, 1024, true>(ctx, pl, x, v, w, dcoef, out, P, F);
         }
     }

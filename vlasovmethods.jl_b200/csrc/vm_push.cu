@@ -254,22 +254,9 @@ static void pass_with_deposit(vm_field* f, vm_particles* p, int pass_mode, int d
     vm_ctx* ctx = f->ctx;
     const int n = f->n;
     const int ncols = n;   // partial rows hold the grid only (the K/M sums live in their own rows)
-    const int pmw = ctx->priv_min_warps > 0 ? ctx->priv_min_warps
-                                            : (pass_mode == MODE_DEPOSIT ? VM_PRIV_MIN_WARPS : VM_PRIV_MIN_WARPS_PUSH);
-    // fused pass on a mesh with more than 16 cells: plan with the 16-fold gather table first -- it only exists in
-    // the lane-private variant, so fall back to the plain table when the plan picks another one
-    bool repg = pass_mode == MODE_PUSH_DEPOSIT && n > 16 && !ctx->no_repg && deposit_mode != VM_DEPOSIT_ATOMIC &&
-                vm_gather_table_doubles(n, f->order, true) * sizeof(double) <= VM_GATHER_TABLE_MAX_BYTES;
-    DepositPlan pl{};
-    if (repg) {
-        try { pl = plan_deposit(ctx, n, f->order - 1, (int)vm_gather_table_doubles(n, f->order, true), deposit_mode, pmw); }
-        catch (const vm_error&) { pl.var = -1; }
-        if (pl.var != VAR_PRIV) repg = false;
-    }
-    if (!repg)
-        pl = plan_deposit(ctx, n, f->order - 1, pass_mode == MODE_PUSH_DEPOSIT ? (int)vm_gather_table_doubles(n, f->order, false) : 0,
-                          deposit_mode, pmw);
-    P.repg = repg ? 1 : 0;
+    const PassPlan pp = plan_pass(ctx, n, f->order, pass_mode, deposit_mode);
+    const DepositPlan& pl = pp.pl;
+    P.repg = pp.repg ? 1 : 0;
     P.map = f->map;
     P.n = p->n;
     P.rep_log2 = pl.rep_log2;
@@ -325,6 +312,37 @@ static void check_pair(vm_field* f, vm_particles* p, const char* who)
 }
 
 extern "C" {
+
+int vm_pass_plan_query(int sm_count, size_t smem_optin_bytes, int n_basis, int order, int pass, int deposit_mode,
+                       vm_pass_plan* out)
+{
+    vm_ctx* ctx__ = nullptr;
+    try {
+        VM_REQUIRE(out != nullptr, "vm_pass_plan_query: out is NULL");
+        VM_REQUIRE(sm_count >= 1 && smem_optin_bytes >= 16 * 1024, "vm_pass_plan_query: bad device description");
+        VM_REQUIRE(n_basis >= 1 && n_basis <= VM_MAX_NBASIS, "vm_pass_plan_query: n_basis out of range");
+        VM_REQUIRE(order >= VM_MIN_ORDER && order <= VM_MAX_ORDER, "vm_pass_plan_query: spline order must be in 2..6");
+        VM_REQUIRE(pass >= 0 && pass <= 2, "vm_pass_plan_query: pass must be 0 (deposit), 1 (fused step) or 2 (drift + deposit)");
+        VM_REQUIRE(deposit_mode == VM_DEPOSIT_DETERMINISTIC || deposit_mode == VM_DEPOSIT_ATOMIC, "vm_pass_plan_query: unknown mode");
+        vm_ctx dev;                      // host-side description only: no CUDA call is made
+        dev.sm_count = sm_count;
+        dev.smem_optin = smem_optin_bytes;
+        const int mode = pass == 0 ? MODE_DEPOSIT : (pass == 1 ? MODE_PUSH_DEPOSIT : MODE_DRIFT_DEPOSIT);
+        const PassPlan pp = plan_pass(&dev, n_basis, order, mode, deposit_mode);
+        const int per_sm = pp.pl.threads * (pp.pl.grid / sm_count);
+        const PassTier t = vm_pass_tier(mode, pp.pl.var, per_sm, 0);
+        out->variant = pp.pl.var;
+        out->replicas = 1 << pp.pl.rep_log2;
+        out->grid = pp.pl.grid;
+        out->threads = pp.pl.threads;
+        out->pairs = t.pairs;
+        out->max_threads = t.max_threads;
+        out->gather_copies = pp.repg ? VM_GATHER_COPIES : 1;
+        out->smem_bytes = pp.pl.smem;
+    }
+    catch (const vm_error& e) { vm_set_error(ctx__, e.what()); return e.code; }
+    return VM_OK;
+}
 
 int vm_deposit(vm_field* f, vm_particles* p, int mode)
 {
