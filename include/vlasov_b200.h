@@ -64,8 +64,15 @@ const char* vm_last_error(vm_ctx* ctx);
 int vm_sync(vm_ctx* ctx);
 int vm_ctx_device_info(vm_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor,
                        size_t* free_bytes, size_t* total_bytes);
-/* Tuning knobs (defaults are chosen from the device and problem size).
- * key: "ctas_per_sm", "threads_per_cta", "replicas" (0 = auto), "profile" (see vm_profile_read). */
+/* Tuning knobs (defaults are chosen from the device and problem size; everything below exists for A/B
+ * measurements and tests -- results are the same to rounding for every setting).
+ * key: "ctas_per_sm", "threads_per_cta", "replicas" (0 = auto): CTA shape / replica grids per warp of the passes;
+ *      "pairs" (0 = auto, 1, 2, 4, 8): pairs of particles in flight per thread in the lane-private passes;
+ *      "priv_min_warps" (0 = auto): fewest warps per SM for which the lane-private deposit is still chosen;
+ *      "no_repg" (1: single field table in the fused pass instead of 16 bank-conflict-free copies);
+ *      "force_match" (1: MATCH.ANY grouping instead of xor-shuffle rounds), "no_uniform_w" (1: always stream the
+ *      weight array), "no_pdl" (1: no programmatic dependent launch), "no_fuse" (1: separate reduce / solve kernels);
+ *      "profile" (see vm_profile_read). */
 int vm_ctx_set_tuning(vm_ctx* ctx, const char* key, int value);
 
 /* Multi-GPU, one process per GPU.  Rank 0 obtains a 128-byte NCCL unique id
