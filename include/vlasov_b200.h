@@ -57,7 +57,10 @@ int vm_abi_version(void);
 
 /* Create a context on CUDA device `device` (ordinal). */
 int vm_ctx_create(int device, vm_ctx** out);
-/* Every particles / field / vspline handle created on a context must be destroyed before the context. */
+/* Handles created on a context should be destroyed before it.  Host languages that finalise objects in no
+ * particular order (Julia, Python at exit) are tolerated: destroying a child handle after its context frees the
+ * child's device memory without touching the context, any other call on it returns VM_ERR_INVALID, and destroying
+ * a context twice is a no-op. */
 int vm_ctx_destroy(vm_ctx* ctx);
 const char* vm_last_error(vm_ctx* ctx);
 /* Block until all work enqueued on the context has finished. */

@@ -568,3 +568,37 @@ def test_interpreter_exit_without_close(tmp_path):
         "print('done')\n" % str(root))
     r = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0 and "done" in r.stdout, (r.returncode, r.stderr[-2000:])
+
+
+def test_handles_outliving_their_context(vm, oracle, rng):
+    """Julia and Python finalise objects in no particular order: a context may be destroyed before its children.
+    The library must then free the orphans without touching the context, refuse to compute with them, accept a
+    second destroy of the context, and leave the device usable."""
+    import ctypes as C
+    L = vm._lib
+    c = vm.Context(0)
+    p = vm.DeviceParticles(c, 1000)
+    f = vm.DeviceField(c, 0.0, 1.0, 4, 16, 0)
+    vs = vm.DeviceVSpline(c, -10.0, 10.0, 41, 4, 1)
+    h = C.c_void_p(c._h.value)
+    assert L.lib().vm_ctx_destroy(h) == 0            # the context goes first
+    assert L.lib().vm_ctx_destroy(h) == 0            # twice: no-op
+    with pytest.raises(vm.VMError) as ei:
+        f.deposit(p, 0)
+    assert ei.value.code == L.VM_ERR_INVALID and "already been destroyed" in str(ei.value)
+    with pytest.raises(vm.VMError):
+        p.upload(np.zeros(1000), np.zeros(1000), np.ones(1000))
+    with pytest.raises(vm.VMError):
+        vs.lb_rhs(p, 1.0, False)
+    assert L.lib().vm_launch_count(h) == 0
+    p.close(); f.close(); vs.close()                 # orphans: freed without the context
+    c._h = C.c_void_p()
+    c2 = vm.Context(0)                               # the device is still usable
+    a, b, n, k = 0.0, 3.0, 16, 4
+    x, v, w = make_particles(rng, 5000, a, b)
+    f2 = vm.DeviceField(c2, a, b, k, n, 0)
+    p2 = vm.DeviceParticles(c2, x.size)
+    p2.upload(x, v, w)
+    f2.deposit(p2, 0)
+    assert relmax(f2.rhs, oracle.deposit_periodic(x, w, a, b, n, k, 0)) <= RTOL
+    c2.close()

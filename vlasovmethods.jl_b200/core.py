@@ -168,9 +168,7 @@ class DeviceParticles:
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:
-            if self.ctx._h.value:                # after its context: destroying would dereference the freed context (only
-                                                 # reachable in interpreter shutdown; the leak ends with the process)
-                L.lib().vm_particles_destroy(self._h)
+            L.lib().vm_particles_destroy(self._h)          # safe in any order: the library tolerates orphaned handles
             self._h = C.c_void_p()
 
     def __del__(self):
@@ -236,9 +234,7 @@ class DeviceField:
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:
-            if self.ctx._h.value:                # after its context: destroying would dereference the freed context (only
-                                                 # reachable in interpreter shutdown; the leak ends with the process)
-                L.lib().vm_field_destroy(self._h)
+            L.lib().vm_field_destroy(self._h)          # safe in any order: the library tolerates orphaned handles
             self._h = C.c_void_p()
 
     def __del__(self):
@@ -336,9 +332,7 @@ class DeviceVSpline:
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:
-            if self.ctx._h.value:                # after its context: destroying would dereference the freed context (only
-                                                 # reachable in interpreter shutdown; the leak ends with the process)
-                L.lib().vm_vspline_destroy(self._h)
+            L.lib().vm_vspline_destroy(self._h)          # safe in any order: the library tolerates orphaned handles
             self._h = C.c_void_p()
 
     def __del__(self):

@@ -4,6 +4,7 @@
 
 #include <cstring>
 #include <mutex>
+#include <unordered_set>
 
 #include "vm_internal.cuh"
 
@@ -16,6 +17,28 @@ void vm_set_error(vm_ctx* ctx, const std::string& msg)
 }
 
 void vm_use(vm_ctx* ctx) { VM_CUDA(cudaSetDevice(ctx->device)); }
+
+namespace {
+std::mutex g_live_mu;
+std::unordered_set<vm_ctx*> g_live;
+}  // namespace
+
+bool vm_ctx_alive(vm_ctx* ctx)
+{
+    std::lock_guard<std::mutex> lk(g_live_mu);
+    return g_live.count(ctx) != 0;
+}
+
+void vm_child_quiesce(vm_ctx* ctx, int device)
+{
+    cudaSetDevice(device);
+    if (vm_ctx_alive(ctx)) {
+        cudaStreamSynchronize(ctx->stream);
+        if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+    } else {
+        cudaDeviceSynchronize();       // orphan: its context (and streams) are gone, the device memory is not
+    }
+}
 
 double* vm_partials(vm_ctx* ctx, size_t elems)
 {
@@ -135,7 +158,7 @@ extern "C" {
 
 int vm_abi_version(void) { return VM_ABI_VERSION; }
 
-const char* vm_last_error(vm_ctx* ctx) { return ctx ? ctx->last_error.c_str() : g_last_error.c_str(); }
+const char* vm_last_error(vm_ctx* ctx) { return (ctx && vm_ctx_alive(ctx)) ? ctx->last_error.c_str() : g_last_error.c_str(); }
 
 int vm_ctx_create(int device, vm_ctx** out)
 {
@@ -170,6 +193,10 @@ int vm_ctx_create(int device, vm_ctx** out)
         VM_CUDA(cudaEventCreateWithFlags(&c->snap_done, cudaEventDisableTiming));
         VM_CUDA(cudaMalloc(&c->ticket, sizeof(unsigned)));
         VM_CUDA(cudaMemset(c->ticket, 0, sizeof(unsigned)));
+        {
+            std::lock_guard<std::mutex> lk(g_live_mu);
+            g_live.insert(c);
+        }
         *out = c;
     }
     catch (const vm_error& e) { vm_set_error(ctx__, e.what()); return e.code; }
@@ -180,6 +207,10 @@ int vm_ctx_create(int device, vm_ctx** out)
 int vm_ctx_destroy(vm_ctx* ctx)
 {
     if (!ctx) return VM_OK;
+    {
+        std::lock_guard<std::mutex> lk(g_live_mu);
+        if (g_live.erase(ctx) == 0) return VM_OK;      // not (or no longer) a context: a second destroy is a no-op
+    }
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     if (ctx->peers_connected)
@@ -355,7 +386,7 @@ int vm_event_elapsed_ms(vm_ctx* ctx, int a, int b, double* ms)
     VM_API_END
 }
 
-unsigned long long vm_launch_count(vm_ctx* ctx) { return ctx ? ctx->launches : 0ull; }
+unsigned long long vm_launch_count(vm_ctx* ctx) { return (ctx && vm_ctx_alive(ctx)) ? ctx->launches : 0ull; }
 
 int vm_profile_read(vm_ctx* ctx, long* launches, double* total_ms)
 {
@@ -476,6 +507,7 @@ int vm_particles_create(vm_ctx* ctx, long n, vm_particles** out)
     *out = nullptr;
     vm_particles* p = new vm_particles();
     p->ctx = ctx;
+    p->device = ctx->device;
     p->n = n;
     size_t bytes = (size_t)(n > 0 ? n : 1) * sizeof(double);
     cudaError_t e1 = cudaMalloc(&p->x, bytes), e2 = cudaMalloc(&p->v, bytes), e3 = cudaMalloc(&p->w, bytes);
@@ -497,11 +529,10 @@ int vm_particles_create(vm_ctx* ctx, long n, vm_particles** out)
 int vm_particles_destroy(vm_particles* p)
 {
     if (!p) return VM_OK;
-    cudaSetDevice(p->ctx->device);
-    cudaStreamSynchronize(p->ctx->stream);
+    vm_child_quiesce(p->ctx, p->device);
     cudaFree(p->x); cudaFree(p->v); cudaFree(p->w);
     if (p->a) cudaFree(p->a);
-    if (p->snap) { cudaStreamSynchronize(p->ctx->copy_stream); cudaFree(p->snap); }
+    if (p->snap) cudaFree(p->snap);
     for (double* q : p->work) if (q) cudaFree(q);
     delete p;
     return VM_OK;

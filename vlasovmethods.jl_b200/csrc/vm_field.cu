@@ -237,6 +237,7 @@ int vm_field_create(vm_ctx* ctx, double a, double b, int order, int n_basis, int
     vm_field* f = new vm_field();
     try {
         f->ctx = ctx;
+        f->device = ctx->device;
         f->a = a; f->b = b; f->order = k; f->n = n; f->shift = index_shift;
         f->h = (b - a) / n;
         f->map.inv_h = (double)((ld)n / ((ld)b - (ld)a));
@@ -285,8 +286,7 @@ int vm_field_create(vm_ctx* ctx, double a, double b, int order, int n_basis, int
 int vm_field_destroy(vm_field* f)
 {
     if (!f) return VM_OK;
-    cudaSetDevice(f->ctx->device);
-    cudaStreamSynchronize(f->ctx->stream);
+    vm_child_quiesce(f->ctx, f->device);
     cudaFree(f->rhs); cudaFree(f->phi); cudaFree(f->dcoef); cudaFree(f->G);
     cudaFree(f->stencil_s); cudaFree(f->diag);
     delete f;

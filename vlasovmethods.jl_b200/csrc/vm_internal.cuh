@@ -74,6 +74,7 @@ struct vm_ctx {
 
 struct vm_particles {
     vm_ctx* ctx = nullptr;
+    int device = 0;
     long n = 0;
     double *x = nullptr, *v = nullptr, *w = nullptr;
     double* a = nullptr;        // lazily allocated per-particle work array (E / vdot)
@@ -100,6 +101,7 @@ struct CellMap {
 
 struct vm_field {
     vm_ctx* ctx = nullptr;
+    int device = 0;
     double a = 0, b = 0, h = 0;
     int order = 0, n = 0, shift = 0;
     CellMap map{};
@@ -113,6 +115,7 @@ struct vm_field {
 
 struct vm_vspline {
     vm_ctx* ctx = nullptr;
+    int device = 0;
     double a = 0, b = 0, h = 0;
     int order = 0, nknots = 0, ncell = 0, npar = 0, nv = 0, bc = 1;
     std::vector<double> mass;          // host nv x nv
@@ -131,6 +134,11 @@ struct vm_vspline {
 
 void vm_set_error(vm_ctx* ctx, const std::string& msg);
 void vm_use(vm_ctx* ctx);                         // cudaSetDevice
+// Contexts are registered while they exist.  Host languages finalise handles in no particular order (Julia and
+// Python at exit), so a child handle can outlive its context: destroying it then must not touch the context, and
+// any other call on it reports VM_ERR_INVALID instead of dereferencing freed memory.
+bool vm_ctx_alive(vm_ctx* ctx);
+void vm_child_quiesce(vm_ctx* ctx, int device);   // device idle for this child: its context's streams, or the whole device
 double* vm_partials(vm_ctx* ctx, size_t elems);   // grow-only device scratch
 double* vm_pinned(vm_ctx* ctx, size_t elems);     // grow-only pinned host scratch
 void vm_allreduce_sum(vm_ctx* ctx, double* dev, size_t count);  // no-op when nranks == 1
@@ -139,9 +147,13 @@ void vm_prof_mark(vm_ctx* ctx);
 void vm_check_peer_error(vm_ctx* ctx);
 bool vm_particles_uniform_weight(vm_particles* p, double* w0);   // classifies w on first use after a change   // after a stream sync: throws if a peer exchange timed out   // records the next event of a start/stop pair when profiling is on
 
-#define VM_API_BEGIN(ctxexpr)          \
-    vm_ctx* ctx__ = (ctxexpr);         \
-    try {                              \
+#define VM_API_BEGIN(ctxexpr)                                                                              \
+    vm_ctx* ctx__ = (ctxexpr);                                                                             \
+    try {                                                                                                  \
+        if (ctx__ && !vm_ctx_alive(ctx__)) {                                                               \
+            ctx__ = nullptr;                                                                               \
+            throw vm_error(VM_ERR_INVALID, "the context of this handle has already been destroyed");       \
+        }                                                                                                  \
         if (ctx__) vm_use(ctx__);
 
 #define VM_API_END                                        \

@@ -796,6 +796,7 @@ int vm_vspline_create(vm_ctx* ctx, double vmin, double vmax, int nknots, int ord
     try {
         const int k = order;
         s->ctx = ctx;
+        s->device = ctx->device;
         s->a = vmin; s->b = vmax; s->order = k; s->nknots = nknots; s->bc = bc;
         s->ncell = nknots - 1;
         s->npar = nknots + k - 2;
@@ -854,8 +855,7 @@ int vm_vspline_create(vm_ctx* ctx, double vmin, double vmax, int nknots, int ord
 int vm_vspline_destroy(vm_vspline* s)
 {
     if (!s) return VM_OK;
-    cudaSetDevice(s->ctx->device);
-    cudaStreamSynchronize(s->ctx->stream);
+    vm_child_quiesce(s->ctx, s->device);
     cudaFree(s->rhs); cudaFree(s->coef); cudaFree(s->minv); cudaFree(s->cellpoly); cudaFree(s->poly);
     cudaFree(s->moments); cudaFree(s->diag);
     delete s;
