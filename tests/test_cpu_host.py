@@ -163,3 +163,22 @@ def test_pass_plans_of_the_benchmarked_meshes(vm):
     for bad in ((0, 4, 1), (16, 7, 1), (16, 4, 3), (5000, 4, 1)):
         with pytest.raises(vm.VMError):
             L.pass_plan(*bad)
+
+
+def test_status_codes_mirror_the_header(vm):
+    header = (ROOT / "include" / "vlasov_b200.h").read_text()
+    body = header[header.index("typedef enum vm_status"):header.index("} vm_status;")]
+    for name, val in re.findall(r"(VM_[A-Z_]+)\s*=\s*(\d+)", body):
+        assert getattr(vm._lib, name) == int(val), name
+    assert len(re.findall(r"VM_[A-Z_]+\s*=\s*\d+", body)) == 7
+
+
+def test_plan_query_and_errors_need_no_device(vm):
+    """Calls that must work on a machine without a GPU: the plan query, and error reporting with a NULL context."""
+    with pytest.raises(vm.VMError) as ei:
+        vm._lib.pass_plan(16, 9, 1)
+    assert ei.value.code == vm._lib.VM_ERR_INVALID and "order" in str(ei.value)
+    lib = vm.lib()
+    assert lib.vm_ctx_destroy(None) == 0 and lib.vm_particles_destroy(None) == 0
+    assert lib.vm_field_destroy(None) == 0 and lib.vm_vspline_destroy(None) == 0
+    assert lib.vm_launch_count(None) == 0 and lib.vm_particles_size(None) == -1

@@ -87,7 +87,7 @@ VM_DEPOSIT_DETERMINISTIC, VM_DEPOSIT_ATOMIC = 0, 1
 VM_RUN_SPLIT_KICK, VM_RUN_FROZEN_FIELD, VM_RUN_ATOMIC_DEPOSIT, VM_RUN_UNFUSED = 1, 2, 4, 8
 (VM_FILL_NORMAL, VM_FILL_BUMP_ON_TAIL, VM_FILL_DOUBLE_MAXWELLIAN, VM_FILL_UNIFORM,
  VM_FILL_SHIFTED_NORMAL_V, VM_FILL_SHIFTED_UNIFORM, VM_FILL_LANDAU) = range(7)
-VM_ERR_NO_DEVICE = 6
+VM_OK, VM_ERR_INVALID, VM_ERR_CUDA, VM_ERR_NOMEM, VM_ERR_NCCL, VM_ERR_UNSUPPORTED, VM_ERR_NO_DEVICE = range(7)   # vm_status
 
 _lib = None
 
