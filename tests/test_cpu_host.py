@@ -182,3 +182,25 @@ def test_plan_query_and_errors_need_no_device(vm):
     assert lib.vm_ctx_destroy(None) == 0 and lib.vm_particles_destroy(None) == 0
     assert lib.vm_field_destroy(None) == 0 and lib.vm_vspline_destroy(None) == 0
     assert lib.vm_launch_count(None) == 0 and lib.vm_particles_size(None) == -1
+
+
+def test_mirror_host_logic_without_a_device(vm):
+    """Pure-Python pieces of the reference-API mirror: time-step counting, snapshot chunking and the example
+    structs' defaults (src/examples/*.jl) with their mapping onto vm_particles_fill."""
+    api = vm.api
+    assert api._ntime((0.0, 20.0), 0.1) == 200 and api._ntime((0.0, 500.0), 1e-2) == 50000      # scripts' values
+    assert api._chunks(200, 0) == [200] and api._chunks(0, 0) == [] and api._chunks(10, 3) == [3, 3, 3, 1]
+    assert sum(api._chunks(12345, 100)) == 12345
+    L = vm._lib
+    assert api._fill_args(api.NormalDistribution()) == (L.VM_FILL_NORMAL, [0.0, 1.0])                       # normal.jl:4
+    assert api._fill_args(api.BumpOnTail()) == (L.VM_FILL_BUMP_ON_TAIL, [0.03, 0.3, 0.1, 0.5, 4.5])          # bumpontail.jl:9
+    assert api._fill_args(api.DoubleMaxwellian()) == (L.VM_FILL_DOUBLE_MAXWELLIAN, [-5.0, 5.0, 3.0])         # doublemaxwellian.jl:5
+    assert api._fill_args(api.UniformDistribution()) == (L.VM_FILL_UNIFORM, [0.0, 1.0, -2.0, 2.0])           # uniform.jl:5
+    assert api._fill_args(api.ShiftedNormalV()) == (L.VM_FILL_SHIFTED_NORMAL_V, [-5.0, 5.0, 2.0])            # shiftednormalv.jl:5
+    assert api._fill_args(api.ShiftedUniformDistribution()) == (L.VM_FILL_SHIFTED_UNIFORM, [0.0, 1.0, -2.0, 2.0, 2.0])
+    with pytest.raises(TypeError):
+        api._fill_args(object())
+    with pytest.raises(NotImplementedError):
+        api.DiffEqIntegrator()
+    b = api.PeriodicBasisBSplineKit((0.0, 1.0), 3, 16)
+    assert (b.order, b.domain) == (3, (0.0, 1.0))
