@@ -356,7 +356,7 @@ def run_gpu(args):
         # mesh-size sweep of the fused step (BASELINE configs[4]: 64-1024 spline modes), same particles, cubic
         p.fill(vm._lib.VM_FILL_BUMP_ON_TAIL, [EPS, KAPPA, ALPHA, SIGMA, V0], SEED, lo, ntot)
         mesh = {}
-        for nh in (32, 64, 128, 256, 1024):
+        for nh in ((32, 64, 128, 256, 1024) if world == 1 else ()):     # single-GPU secondary number
             f2 = vm.DeviceField(ctx, 0.0, L_DOMAIN, ORDER, nh, 0)
             f2.run(p, DT, 3, 0, flags, 1.0)
             t = timed(lambda: f2.run(p, DT, 10, 0, flags, 1.0), 2) / 10
