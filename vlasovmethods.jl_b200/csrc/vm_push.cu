@@ -271,7 +271,8 @@ static void pass_with_deposit(vm_field* f, vm_particles* p, int pass_mode, int d
     } else {
         out = vm_partials(ctx, (size_t)pl.grid * ncols);
         const size_t gdoubles = ((size_t)(n + f->order - 1) << pl.rep_log2) * (size_t)(pl.var == VAR_ATOMIC ? 1 : pl.threads / 32);
-        if (n <= VM_FUSE_MAX_N && !ctx->no_fuse && gdoubles >= (size_t)3 * n + 1) {
+        // the last-CTA finish works with one thread per basis function (hand-tuned CTA shapes may be smaller)
+        if (n <= VM_FUSE_MAX_N && !ctx->no_fuse && gdoubles >= (size_t)3 * n + 1 && pl.threads >= n) {
             F.mode = (want_solve && ctx->nranks == 1) ? FINISH_REDUCE_SOLVE : FINISH_REDUCE;
             F.ticket = ctx->ticket;
             F.rhs = f->rhs; F.G = f->G; F.phi = f->phi; F.dcoef = f->dcoef; F.inv_h = f->map.inv_h;

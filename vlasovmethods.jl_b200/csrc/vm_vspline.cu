@@ -649,7 +649,8 @@ VDepSetup vdep_setup(vm_vspline* s, int extra_doubles)
     d.pl = plan_deposit(ctx, s->npar, 0, extra_doubles, VM_DEPOSIT_DETERMINISTIC);
     d.out = vm_partials(ctx, (size_t)d.pl.grid * s->npar);
     const size_t gdoubles = ((size_t)s->npar << d.pl.rep_log2) * (size_t)(d.pl.threads / 32);
-    if (s->npar <= VM_FUSE_MAX_N && !ctx->no_fuse && d.pl.var != VAR_ATOMIC && gdoubles >= (size_t)2 * s->npar + 1) {
+    if (s->npar <= VM_FUSE_MAX_N && !ctx->no_fuse && d.pl.var != VAR_ATOMIC && gdoubles >= (size_t)2 * s->npar + 1 &&
+        d.pl.threads >= s->npar) {     // the finish works with one thread per basis function
         d.F.mode = FINISH_REDUCE;           // last CTA sums the per-CTA rows in a fixed order
         d.F.ticket = ctx->ticket;
         d.F.rhs = s->rhs;
