@@ -17,6 +17,10 @@ A "step" = one Strang step: E gather -> kick -> drift -> charge deposition -> al
            which streams the weight array as for per-particle weights), timed per
            launch with CUDA event brackets over a second run of the same K steps (the brackets defeat
            the programmatic-dependent-launch overlap, so they stay out of the `value` region).
+`deposit`: the deposit-only pass (projection! alone) with the uniform weight and with the weight array streamed.
+`secondary`: LB / CLB right-hand sides and the CLB RK438 step at the same particle count (configs[2], [3]) and, on
+           one GPU, the fused step on meshes of 32 ... 1024 cells (configs[4]).
+`cpu_baseline`: the C restatement of the reference algorithm on the host cores (N = 1 only, bounded sample).
 """
 from __future__ import annotations
 
