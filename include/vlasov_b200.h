@@ -131,7 +131,7 @@ int vm_host_alloc(size_t bytes, void** out);   /* page-locked host memory */
 int vm_host_free(void* ptr);
 
 /* Device-side synthetic loads reproducing the *distributions* of
- * src/examples/*.jl (the reference draws from Julia's unseeded global RNG, so
+ * the example files under src/examples (the reference draws from Julia's unseeded global RNG, so
  * streams cannot match).  Counter-based Philox4x32-10 keyed by
  * (seed, global particle index): the load is independent of the sharding.
  * first_index/total_n: this shard holds particles first_index .. first_index+n-1

@@ -204,3 +204,26 @@ def test_mirror_host_logic_without_a_device(vm):
         api.DiffEqIntegrator()
     b = api.PeriodicBasisBSplineKit((0.0, 1.0), 3, 16)
     assert (b.order, b.domain) == (3, (0.0, 1.0))
+
+
+def test_header_is_plain_c_and_links_from_c(vm, tmp_path):
+    """The boundary is a C ABI: include/vlasov_b200.h must compile as strict C11 (no C++-isms, no warnings), the
+    example host program must link against libvlasov_b200.so without any Python or torch in the process, and
+    without a GPU it must fail loudly with the library's own message (exit status 3)."""
+    import shutil
+    import torch
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    pkg = ROOT / "vlasovmethods.jl_b200"
+    exe = tmp_path / "landau"
+    cmd = ["gcc", "-std=c11", "-Wall", "-Wextra", "-pedantic", "-Werror", f"-I{ROOT / 'include'}",
+           str(ROOT / "examples" / "landau_damping.c"), "-o", str(exe), f"-L{pkg}", "-lvlasov_b200", "-lm",
+           f"-Wl,-rpath,{pkg}"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    if torch.cuda.is_available():
+        r = subprocess.run([str(exe), "200000", "32", "60"], capture_output=True, text=True, timeout=120)
+        assert r.returncode == 0 and "damping rate" in r.stdout, r.stdout[-500:] + r.stderr[-500:]
+    else:
+        r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=60)
+        assert r.returncode == 3 and "no CPU path" in r.stderr, (r.returncode, r.stderr)
