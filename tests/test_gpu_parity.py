@@ -602,3 +602,25 @@ def test_handles_outliving_their_context(vm, oracle, rng):
     f2.deposit(p2, 0)
     assert relmax(f2.rhs, oracle.deposit_periodic(x, w, a, b, n, k, 0)) <= RTOL
     c2.close()
+
+
+@pytest.mark.parametrize("n", [64, 128])
+def test_split_kick_on_midsize_meshes(vm, oracle, rng, n):
+    """The two-half-kick form of the new-API Strang step (VM_RUN_SPLIT_KICK) in the deep-pipeline tiers of the
+    fused pass (n_h = 64: 4 pairs in flight, n_h = 128: 8 pairs) against the oracle's Strang step."""
+    c = vm.Context(0)
+    a, b, k = 0.0, 2 * math.pi / 0.3, 4
+    npart = 300_001
+    x = rng.uniform(a, b, npart); v = rng.standard_normal(npart); w = np.full(npart, (b - a) / npart)
+    shift = oracle.bspline_shift_bsplinekit(k)
+    S = oracle.periodic_stiffness(a, b, n, k, shift)
+    fld = vm.DeviceField(c, a, b, k, n, shift)
+    p = vm.DeviceParticles(c, npart)
+    xo, vo = x.copy(), v.copy()
+    for _ in range(4):
+        oracle.vp_strang_step(xo, vo, w, 0.1, a, b, n, k, shift, S)
+    p.upload(x, v, w)
+    fld.run(p, 0.1, 4, 0, 1, 1.0)
+    xg, vg, _ = p.download(w=False)
+    assert np.max(np.abs(xg - xo)) <= 1e-11 and np.max(np.abs(vg - vo)) <= 1e-11
+    fld.close(); p.close(); c.close()
