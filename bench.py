@@ -20,7 +20,13 @@ A "step" = one Strang step: E gather -> kick -> drift -> charge deposition -> al
 `deposit`: the deposit-only pass (projection! alone) with the uniform weight and with the weight array streamed.
 `secondary`: LB / CLB right-hand sides and the CLB RK438 step at the same particle count (configs[2], [3]) and, on
            one GPU, the fused step on meshes of 32 ... 1024 cells (configs[4]).
-`cpu_baseline`: the C restatement of the reference algorithm on the host cores (N = 1 only, bounded sample).
+`cpu_baseline`: the C restatement of the reference algorithm on the host cores (N = 1 only), on the SAME 1e8-particle
+           arrays as the GPU arm's workload (a bounded number of steps), as is `--impl reference`.
+`parity`   : a 40 000-particle sharded run on the same ranks checked against the CPU oracle (checker only) and the
+           field coefficients compared bitwise across ranks -- the multi-GPU correctness record of the driver runs.
+`value`    : median over `repeats` timed regions of K steps each (min / max alongside); before every region the ranks
+           are aligned on the device by one untimed fused step (its in-kernel exchange waits for the slowest rank).
+`ceilings` : tools/microbench/peaks (fp64 FMA rate, shared-memory wavefront rate, copy bandwidth) run on the same GPU.
 """
 from __future__ import annotations
 
@@ -125,16 +131,28 @@ def native_oracle():
         return orc, orc.lib()
 
 
-def sample_particles(n, seed=SEED):
-    """Bump-on-tail load for the CPU arm (numpy; same distribution as the device fill)."""
-    rng = np.random.default_rng(seed)
-    u = rng.uniform(size=n)
+def _sample_chunk(args):
+    lo, hi, seed = args
+    rng = np.random.default_rng([seed, lo])
+    m = hi - lo
+    u = rng.uniform(size=m)
     x = u * L_DOMAIN
-    for _ in range(40):
+    for _ in range(8):          # Newton on the CDF x - (eps/kappa) sin(kappa x) = u L: eps = 0.03, quadratic convergence
         x -= (x - (EPS / KAPPA) * np.sin(KAPPA * x) - u * L_DOMAIN) / (1 - EPS * np.cos(KAPPA * x))
-    v = rng.standard_normal(n)
-    tail = rng.uniform(size=n) > 1 - ALPHA
+    v = rng.standard_normal(m)
+    tail = rng.uniform(size=m) > 1 - ALPHA
     v[tail] = v[tail] * SIGMA + V0
+    return lo, x, v
+
+
+def sample_particles(n, seed=SEED):
+    """Bump-on-tail load for the CPU arm (numpy, chunks on all host threads; same distribution as the device fill)."""
+    from concurrent.futures import ThreadPoolExecutor
+    x, v = np.empty(n), np.empty(n)
+    step = 2_000_000
+    with ThreadPoolExecutor(max_workers=host_threads()) as ex:
+        for lo, xs, vs in ex.map(_sample_chunk, [(lo, min(n, lo + step), seed) for lo in range(0, n, step)]):
+            x[lo:lo + xs.size], v[lo:lo + vs.size] = xs, vs
     w = np.full(n, L_DOMAIN / n)
     return x, v, w
 
@@ -147,11 +165,10 @@ def host_threads():
         return max(1, os.cpu_count() or 1)
 
 
-def cpu_baseline(target_seconds=12.0):
-    """C restatement of the reference algorithm on the host cores, bounded sample of the same workload."""
+def cpu_baseline(n_s=N_TOTAL, target_seconds=12.0):
+    """C restatement of the reference algorithm on the host cores, on the workload's own particle count."""
     orc, nlib = native_oracle()
     threads = host_threads()
-    n_s = 4_000_000
     x, v, w = sample_particles(n_s)
     t0 = time.perf_counter()
     orc.baseline_vp_steps(x, v, w, DT, 1, 0.0, L_DOMAIN, N_BASIS, ORDER, 0, threads, nlib)   # warm-up + calibration
@@ -166,8 +183,8 @@ def cpu_baseline(target_seconds=12.0):
     orc.baseline_vp_steps(x[:n_1].copy(), v[:n_1].copy(), w[:n_1].copy(), DT, 2, 0.0, L_DOMAIN, N_BASIS, ORDER, 0, 1, nlib)
     dt_1 = time.perf_counter() - t0
     return {"value": n_s * steps / dt_all, "unit": "particle-steps/s", "cores": threads, "kind": "port",
-            "sample": f"{n_s} particles x {steps} Strang steps (2 deposits+2 solves+2 gathers each, as the reference), "
-                      f"OpenMP {threads} threads, C restatement of the reference algorithm (Julia unavailable)",
+            "sample": f"{n_s} particles (the full workload) x {steps} Strang steps (2 deposits+2 solves+2 gathers each, as the "
+                      f"reference), OpenMP {threads} threads, C restatement of the reference algorithm (Julia unavailable)",
             "single_thread_value": n_1 * 2 / dt_1}
 
 
@@ -177,7 +194,7 @@ def run_reference(args):
         return
     orc, nlib = native_oracle()
     threads = host_threads()
-    n_s = 4_000_000                              # bounded sample of the 1e8-particle workload per step
+    n_s = args.particles                         # the workload itself: all particles, every step
     x, v, w = sample_particles(n_s)
     for _ in range(args.warmup):
         orc.baseline_vp_steps(x, v, w, DT, 1, 0.0, L_DOMAIN, N_BASIS, ORDER, 0, threads, nlib)
@@ -185,13 +202,15 @@ def run_reference(args):
     orc.baseline_vp_steps(x, v, w, DT, args.steps, 0.0, L_DOMAIN, N_BASIS, ORDER, 0, threads, nlib)
     dt = time.perf_counter() - t0
     val = n_s * args.steps / dt
-    sample = (f"{n_s}-particle sample of the 1e8 workload per step, OpenMP {threads} threads; "
+    sample = (f"all {n_s} particles of the workload per step, OpenMP {threads} threads; "
               "C restatement of the reference algorithm (Julia toolchain unavailable)")
+    cfg = workload_config(args.gpus)
+    cfg["particles_total"] = n_s
     emit(({
         "impl": "reference", "metric": "particle-steps/sec", "value": val, "unit": "particle-steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args.gpus),
+        "config": cfg,
         "cpu_baseline": {"value": val, "unit": "particle-steps/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -204,6 +223,75 @@ def workload_config(ngpus):
 
 
 # ------------------------------------------------------------------ GPU arm --
+def device_ceilings():
+    """tools/microbench/peaks (built by __graft_entry__.build()): fp64 FMA rate, conflict-free shared-memory
+    read-modify-write wavefront rate, copy bandwidth of THIS GPU -- the non-HBM ceilings of the particle passes."""
+    import subprocess
+    exe = ROOT / "tools" / "microbench" / "peaks"
+    if not exe.exists():
+        return {"error": "tools/microbench/peaks not built"}
+    try:
+        r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+        return json.loads(r.stdout.strip().splitlines()[-1])
+    except Exception as exc:
+        return {"error": repr(exc)}
+
+
+def parity_check(vm, ctx, rank, world, dist):
+    """A small sharded run on these very ranks against the CPU oracle (checker only): 40 001 particles, 6 fused steps
+    + diagnostics on meshes of 16 and 256 cells, a CLB right-hand side; phi compared bitwise across ranks."""
+    from oracle import vm_oracle as orc
+    import torch
+    rng = np.random.default_rng(5)
+    k, npart, dt, nt = 4, 40001, 0.1, 6
+    a, b = 0.0, L_DOMAIN
+    x = rng.uniform(a, b, npart); v = rng.standard_normal(npart); w = np.full(npart, (b - a) / npart)
+    lo, hi = vm.shard_bounds(npart, rank, world)
+    out = {"particles": npart, "steps": nt, "max_rel": 0.0, "ranks_bitwise": True, "meshes": [16, 256]}
+    p = vm.DeviceParticles(ctx, hi - lo)
+    for n in out["meshes"]:
+        fld = vm.DeviceField(ctx, a, b, k, n, 0)
+        p.upload(x[lo:hi], v[lo:hi], w[lo:hi])
+        diag = fld.run(p, dt, nt, 2, 0, 1.0)
+        xg, vg, _ = p.download(w=False)
+        phi = fld.coefficients
+        err = 0.0
+        if rank == 0 or world <= 8:      # every rank checks its own shard against the (replicated) oracle run
+            S = orc.periodic_stiffness(a, b, n, k, 0)
+            xo, vo = x.copy(), v.copy()
+            dref, phiref = orc.integrate_vp(xo, vo, w, dt, 1.0, nt, 2, a, b, n, k, 0, S, want_phi=True)
+            err = max(float(np.max(np.abs(xg - xo[lo:hi])) / (b - a)), float(np.max(np.abs(vg - vo[lo:hi])) / np.max(np.abs(vo))),
+                      float(np.max(np.abs(diag[:, :3] - dref) / np.max(np.abs(dref), axis=0))),
+                      float(np.max(np.abs(phi - phiref[-1])) / np.max(np.abs(phiref[-1]))))
+        same = True
+        if world > 1:
+            t = torch.from_numpy(phi.copy()); ref = t.clone(); dist.broadcast(ref, src=0)
+            same = bool(torch.equal(t, ref))
+            red = torch.tensor([err, 0.0 if same else 1.0], dtype=torch.float64)
+            dist.all_reduce(red, op=dist.ReduceOp.MAX)
+            err, same = float(red[0]), red[1] == 0.0
+        out["max_rel"] = max(out["max_rel"], err)
+        out["ranks_bitwise"] = bool(out["ranks_bitwise"] and same)
+        fld.close()
+    # v-space: sharded conservative Lenard-Bernstein right-hand side
+    vs = vm.DeviceVSpline(ctx, -10.0, 10.0, 41, 4, 1)
+    wv = np.full(npart, 1.0 / npart)
+    p.upload(v=v[lo:hi], w=wv[lo:hi])
+    vdot = vs.lb_rhs(p, 1.0, True)
+    M = orc.dirichlet_mass(-10.0, 10.0, 41, 4)
+    vref, _, _ = orc.lb_rhs(v, wv, -10.0, 10.0, 41, 4, M, 1.0, True)
+    e = float(np.max(np.abs(vdot - vref[lo:hi])) / np.max(np.abs(vref)))
+    if world > 1:
+        red = torch.tensor([e], dtype=torch.float64)
+        dist.all_reduce(red, op=dist.ReduceOp.MAX)
+        e = float(red[0])
+    out["clb_rhs_max_rel"] = e
+    out["tolerance"] = 1e-10
+    out["ok"] = bool(out["max_rel"] <= 1e-10 and e <= 1e-10 and out["ranks_bitwise"])
+    vs.close(); p.close()
+    return out
+
+
 def run_gpu(args):
     from __graft_entry__ import load_package
     vm = load_package()
@@ -213,6 +301,12 @@ def run_gpu(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    try:        # one core set per rank: pinned host buffers are first touched (and stay) near the cores that fill them
+        cores = sorted(os.sched_getaffinity(0))
+        per = max(1, len(cores) // max(world, 1))
+        os.sched_setaffinity(0, set(cores[local * per:(local + 1) * per]) or set(cores))
+    except Exception:
+        pass
     if world > 1:
         dist.init_process_group(backend="gloo")      # host-side rendezvous/barrier only
     ctx = vm.init_distributed_context(local, peer_exchange=not args.no_peer)
@@ -229,12 +323,25 @@ def run_gpu(args):
         if world > 1:
             dist.barrier()
 
-    def max_over_ranks(x):
+    def over_ranks(x, op):
         if world == 1:
             return x
         t = torch.tensor([x], dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=op)
         return float(t[0])
+
+    def max_over_ranks(x):
+        return over_ranks(x, dist.ReduceOp.MAX) if world > 1 else x
+
+    def min_over_ranks(x):
+        return over_ranks(x, dist.ReduceOp.MIN) if world > 1 else x
+
+    parity = None
+    if not args.no_parity:
+        try:
+            parity = parity_check(vm, ctx, rank, world, dist)
+        except Exception as exc:
+            parity = {"ok": False, "error": repr(exc)}
 
     fld = vm.DeviceField(ctx, 0.0, L_DOMAIN, ORDER, N_BASIS, 0)
     p = vm.DeviceParticles(ctx, nloc)
@@ -244,75 +351,117 @@ def run_gpu(args):
         ctx.set_tuning("no_uniform_w", 1)
     ALG_BYTES_PER_PARTICLE = ALG_BYTES_GENERAL_W if args.general_weights else ALG_BYTES_UNIFORM_W
     dep_bytes = ALG_BYTES_PER_PARTICLE - 24      # deposit-only pass: read x (+ w)
+    peak, peak_src = peaks()
 
     # ---------------- device-resident timing ----------------
-    # Region A (value): K steps, nothing but the hot path on the stream.
+    # Region A (value): K steps, nothing but the hot path on the stream; `repeats` such regions, median reported.
+    # Before each region one untimed fused step aligns the ranks ON THE DEVICE (its exchange waits for the slowest
+    # rank): a host barrier alone leaves the ranks' streams hundreds of microseconds apart, which the first in-kernel
+    # exchange of a 2 ms region would charge to the earliest rank.
+    def timed_region(field, steps, e0, e1):
+        barrier()
+        field.run(p, DT, 1, 0, flags, 1.0)           # untimed: device-side alignment of the ranks
+        lc = ctx.launch_count()
+        ctx.event_record(e0)
+        field.run(p, DT, steps, 0, flags, 1.0)
+        ctx.event_record(e1)
+        lc = ctx.launch_count() - lc
+        barrier()
+        loc = ctx.event_elapsed_ms(e0, e1)
+        return max_over_ranks(loc), min_over_ranks(loc), lc
+
     fld.run(p, DT, args.warmup, 0, flags, 1.0)
     sampler = ClockSampler(physical_gpu_index(local))
     barrier()
-    l0 = ctx.launch_count()
     sampler.start()
-    ctx.event_record(0)
-    fld.run(p, DT, args.steps, 0, flags, 1.0)
-    ctx.event_record(1)
-    barrier()
+    regions = [timed_region(fld, args.steps, 0, 1) for _ in range(args.repeats)]
     clocks = sampler.stop()
-    ms = max_over_ranks(ctx.event_elapsed_ms(0, 1))
-    launches = ctx.launch_count() - l0
+    launches = regions[0][2]                                     # kernels launched inside ONE timed region of K steps
+    ms_all = sorted(r[0] for r in regions)
+    ms = float(np.median(ms_all))
     value = ntot * args.steps / (ms * 1e-3)
+    timing = {"repeats": args.repeats, "ms_per_step_median": ms / args.steps, "ms_per_step_min": ms_all[0] / args.steps,
+              "ms_per_step_max": ms_all[-1] / args.steps,
+              "rank_min_over_max_elapsed": min(r[1] / r[0] for r in regions),
+              "aligned_by": "one untimed fused step after the host barrier"}
+
     # Region B (roofline): the same K steps again with every launch of the dominant kernel bracketed by
     # CUDA events on the library's stream (the brackets serialise the launches, so they are kept out of
     # region A where programmatic dependent launch overlaps consecutive kernels).
-    ctx.set_tuning("profile", 1)
-    ctx.profile_read()
-    barrier()
-    ctx.event_record(6)
-    fld.run(p, DT, args.steps, 0, flags, 1.0)
-    ctx.event_record(7)
-    barrier()
-    ms_bracketed = max_over_ranks(ctx.event_elapsed_ms(6, 7))
-    kn, kms = ctx.profile_read()
-    ctx.set_tuning("profile", 0)
+    def bracketed(field, steps, alg_bytes, kernel):
+        ctx.set_tuning("profile", 1)
+        ctx.profile_read()
+        barrier()
+        ctx.event_record(6)
+        field.run(p, DT, steps, 0, flags, 1.0)
+        ctx.event_record(7)
+        barrier()
+        ms_b = max_over_ranks(ctx.event_elapsed_ms(6, 7))
+        kn, kms = ctx.profile_read()
+        ctx.set_tuning("profile", 0)
+        if kn <= 0:
+            return None
+        achieved = alg_bytes * nloc / (kms / kn * 1e-3) / 1e9
+        return {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "peak_source": f"of {peak_src}", "launches_timed": kn, "avg_launch_ms": kms / kn,
+                "ms_per_step_with_brackets": ms_b / steps, "algorithmic_bytes_per_launch": alg_bytes * nloc,
+                "algorithmic_bytes_per_particle": alg_bytes}
 
-    peak, peak_src = peaks()
-    roofline = None
-    if kn > 0:
-        achieved = ALG_BYTES_PER_PARTICLE * nloc / (kms / kn * 1e-3) / 1e9
-        traffic = None
+    def traffic_of(general):
         tf = ROOT / "profiles" / "traffic.json"
-        if tf.exists():
-            try:
-                key = "k_vp_pass_push_deposit_bytes_per_particle" + ("" if args.general_weights else "_uniform_w")
-                traffic = json.loads(tf.read_text()).get(key)
-                traffic = traffic * nloc if traffic is not None else None
-            except Exception:
-                traffic = None
-        roofline = {"bound": "hbm", "kernel": "k_vp_pass<4,PRIV,PUSH_DEPOSIT>", "achieved": achieved, "peak": peak,
-                    "unit": "GB/s", "frac": achieved / peak, "peak_source": f"of {peak_src}",
-                    "traffic": traffic, "launches_timed": kn, "avg_launch_ms": kms / kn,
-                    "ms_per_step_with_brackets": ms_bracketed / args.steps,
-                    "algorithmic_bytes_per_launch": ALG_BYTES_PER_PARTICLE * nloc,
-                    "algorithmic_bytes_per_particle": ALG_BYTES_PER_PARTICLE,
-                    "weights": "per-particle array streamed" if args.general_weights else
-                               "uniform (w = L/N for every particle, as every sampler of the reference produces): passed as a kernel parameter, not read from HBM"}
+        try:
+            key = "k_vp_pass_push_deposit_bytes_per_particle" + ("" if general else "_uniform_w")
+            t = json.loads(tf.read_text()).get(key)
+            return t * nloc if t is not None else None
+        except Exception:
+            return None
+
+    roofline = bracketed(fld, args.steps, ALG_BYTES_PER_PARTICLE, "k_vp_pass<4,PRIV,PUSH_DEPOSIT>")
+    if roofline:
+        roofline["traffic"] = traffic_of(args.general_weights)
+        roofline["traffic_source"] = "ncu --set full capture of this kernel (profiles/traffic.json), not re-measured in this run"
+        roofline["weights"] = ("per-particle array streamed" if args.general_weights else
+                               "uniform (w = L/N for every particle, as every sampler of the reference produces): passed as a kernel parameter, not read from HBM")
+
+    # the same step with the weight array streamed (SURVEY 8(d)'s 40 B/particle-step), beside the 32 B headline
+    general = None
+    if not args.general_weights:
+        ctx.set_tuning("no_uniform_w", 1)
+        fld.run(p, DT, 3, 0, flags, 1.0)
+        g_all = sorted(timed_region(fld, args.steps, 4, 5)[0] for _ in range(3))
+        g_ms = float(np.median(g_all))
+        g_roof = bracketed(fld, args.steps, ALG_BYTES_GENERAL_W, "k_vp_pass<4,PRIV,PUSH_DEPOSIT> (weights streamed)")
+        if g_roof:
+            g_roof["traffic"] = traffic_of(True)
+        general = {"algorithmic_bytes_per_particle": ALG_BYTES_GENERAL_W, "ms_per_step": g_ms / args.steps,
+                   "particle_steps_per_s": ntot * args.steps / (g_ms * 1e-3),
+                   "step_hbm_frac": ALG_BYTES_GENERAL_W * nloc * args.steps / (g_ms * 1e-3) / 1e9 / peak, "roofline": g_roof}
+        ctx.set_tuning("no_uniform_w", 0)
 
     # ---------------- end-to-end through host buffers ----------------
     hx = torch.empty(nloc, dtype=torch.float64).pin_memory()
     hv = torch.empty(nloc, dtype=torch.float64).pin_memory()
-    hw = torch.empty(nloc, dtype=torch.float64).pin_memory()
     p.fill(vm._lib.VM_FILL_BUMP_ON_TAIL, [EPS, KAPPA, ALPHA, SIGMA, V0], SEED, lo, ntot)
-    p.download(out=(hx.numpy(), hv.numpy(), hw.numpy()))
+    p.download(w=False, out=(hx.numpy(), hv.numpy(), None))
     e2e_steps = args.steps
+    w0 = L_DOMAIN / ntot
+    hw = None
+    if args.general_weights:
+        hw = torch.full((nloc,), w0, dtype=torch.float64).pin_memory()
 
     def e2e_once():
-        p.upload(hx.numpy(), hv.numpy(), hw.numpy())                     # H2D 24 B/particle
+        if hw is None:
+            p.upload(hx.numpy(), hv.numpy(), None)                       # H2D 16 B/particle
+            p.set_uniform_weight(w0)                                     # w = L/N declared, not uploaded
+        else:
+            p.upload(hx.numpy(), hv.numpy(), hw.numpy())                 # H2D 24 B/particle
         d = fld.run(p, DT, e2e_steps, e2e_steps, flags, 1.0)             # K steps + [W,K,M] rows read back
         p.download(w=False, out=(hx.numpy(), hv.numpy(), None))          # D2H 16 B/particle
         return d
 
     e2e_once()                                                           # warm-up (page-locks, allocations)
     p.fill(vm._lib.VM_FILL_BUMP_ON_TAIL, [EPS, KAPPA, ALPHA, SIGMA, V0], SEED, lo, ntot)
-    p.download(out=(hx.numpy(), hv.numpy(), hw.numpy()))
+    p.download(w=False, out=(hx.numpy(), hv.numpy(), None))
     barrier()
     t0 = time.perf_counter()
     ctx.event_record(2)
@@ -321,10 +470,12 @@ def run_gpu(args):
     barrier()
     wall = time.perf_counter() - t0
     e2e_ms = max_over_ranks(max(ctx.event_elapsed_ms(2, 3), 0.0))
+    h2d = (24 if hw is not None else 16) * ntot
     e2e = {"value": ntot * e2e_steps / (e2e_ms * 1e-3), "unit": "particle-steps/s",
-           "h2d_bytes_per_step": 24 * ntot / e2e_steps, "d2h_bytes_per_step": (16 * ntot + 2 * 32 * world) / e2e_steps,
+           "h2d_bytes_per_step": h2d / e2e_steps, "d2h_bytes_per_step": (16 * ntot + 2 * 32 * world) / e2e_steps,
            "steps_per_call": e2e_steps, "ms_per_call": e2e_ms, "wall_ms": wall * 1e3,
-           "what": "upload x,v,w from pinned host arrays + K fused steps + diagnostics read-back + download x,v "
+           "what": "upload x,v from pinned host arrays (+ vm_particles_set_uniform_weight: w = L/N is declared, not "
+                   "uploaded) + K fused steps + diagnostics read-back + download x,v "
                    "(vm_particles_upload_soa / vm_vp_run / vm_particles_download_soa)",
            "energy_drift": float(abs((diag[-1, 0] + diag[-1, 1]) - (diag[0, 0] + diag[0, 1])) / (diag[0, 0] + diag[0, 1]))}
 
@@ -336,19 +487,35 @@ def run_gpu(args):
         ctx.event_record(9)
         return max_over_ranks(ctx.event_elapsed_ms(8, 9)) / reps
 
+    ceil = device_ceilings() if (rank == 0 and not args.no_ceilings) else None
+    sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+    sm_count = ctx.device_info()["sm_count"]
+
+    def lsu_frac(wavefronts_per_warp_particle, ms_):
+        """Shared-memory data-pipe utilisation implied by the wavefront model (profiles/README.md section 7) at the
+        SM clock sampled in region A, against the measured conflict-free read-modify-write rate of this GPU."""
+        if not ceil or "smem_rmw_wavefronts_per_clk_per_sm" not in ceil:
+            return None
+        wf = wavefronts_per_warp_particle * (nloc / 32.0) / sm_count
+        rate = wf / (ms_ * 1e-3 * sm_mhz * 1e6)
+        return {"wavefronts_per_warp_of_particles": wavefronts_per_warp_particle, "achieved_wf_per_clk_per_sm": rate,
+                "peak_wf_per_clk_per_sm": ceil["smem_rmw_wavefronts_per_clk_per_sm"],
+                "frac": rate / ceil["smem_rmw_wavefronts_per_clk_per_sm"], "sm_mhz_assumed": sm_mhz}
+
     dep_ms = timed(lambda: fld.deposit(p, 0), 10)            # projection!(potential, dist) alone
     ctx.set_tuning("no_uniform_w", 1)                        # same pass with the weight array streamed (16 B/particle)
     dep_ms_gw = timed(lambda: fld.deposit(p, 0), 10)
     ctx.set_tuning("no_uniform_w", 1 if args.general_weights else 0)
     deposit = {"kernel": "k_vp_pass<4,PRIV,DEPOSIT>", "ms": dep_ms, "GBps": dep_bytes * nloc / dep_ms / 1e6,
                "frac": dep_bytes * nloc / dep_ms / 1e6 / peak, "algorithmic_bytes_per_particle": dep_bytes,
+               "bound": "lsu" if dep_bytes == 8 else "hbm", "lsu": lsu_frac(18.0, dep_ms),
                "particles_per_s": nloc * world / dep_ms * 1e3,
-               "per_particle_weights": {"ms": dep_ms_gw, "algorithmic_bytes_per_particle": 16,
+               "per_particle_weights": {"ms": dep_ms_gw, "algorithmic_bytes_per_particle": 16, "bound": "hbm",
                                         "GBps": 16 * nloc / dep_ms_gw / 1e6, "frac": 16 * nloc / dep_ms_gw / 1e6 / peak},
                "note": "with the uniform weight of this workload the pass reads 8 B/particle and is bound by the L1TEX/"
                        "shared-memory data pipe, not by HBM: 16 wavefronts per warp of particles for the K=4 read-modify-"
-                       "writes of the lane-private replicas + 2 for the loads = 93 % of the LSU wavefront peak (ncu, "
-                       "profiles/README.md); with per-particle weights (16 B/particle) see per_particle_weights",
+                       "writes of the lane-private replicas + 2 for the loads (`lsu`: against the measured wavefront rate "
+                       "of tools/microbench/peaks); with per-particle weights (16 B/particle) see per_particle_weights",
                "shared_atomics": 0, "mode": "deterministic (lane-private replicas)"}
     secondary = None
     if not args.no_secondary:
@@ -360,10 +527,10 @@ def run_gpu(args):
         # mesh-size sweep of the fused step (BASELINE configs[4]: 64-1024 spline modes), same particles, cubic
         p.fill(vm._lib.VM_FILL_BUMP_ON_TAIL, [EPS, KAPPA, ALPHA, SIGMA, V0], SEED, lo, ntot)
         mesh = {}
-        for nh in ((32, 64, 128, 256, 1024) if world == 1 else ()):     # single-GPU secondary number
+        for nh in ((32, 64, 128, 256, 512, 1024) if world == 1 else (64, 256, 1024)):
             f2 = vm.DeviceField(ctx, 0.0, L_DOMAIN, ORDER, nh, 0)
             f2.run(p, DT, 3, 0, flags, 1.0)
-            t = timed(lambda: f2.run(p, DT, 10, 0, flags, 1.0), 2) / 10
+            t = float(np.median([timed_region(f2, 10, 10, 11)[0] for _ in range(3)])) / 10
             mesh[str(nh)] = {"ms_per_step": t, "particle_steps_per_s": ntot / t * 1e3,
                              "step_hbm_frac": ALG_BYTES_PER_PARTICLE * nloc / t / 1e6 / peak}
             f2.close()
@@ -372,13 +539,17 @@ def run_gpu(args):
                      "weights": "uniform w = 1/N: not streamed (8 B less per deposit pass)",
                      "lb_rhs_evals_per_s": ntot / lb * 1e3, "lb_rhs_hbm_frac": 24 * nloc / lb / 1e6 / peak,
                      "clb_rhs_evals_per_s": ntot / clb * 1e3, "clb_rhs_hbm_frac": 32 * nloc / clb / 1e6 / peak,
-                     "clb_rk438_particle_steps_per_s": ntot / rk * 1e3, "clb_rk438_hbm_frac": 168 * nloc / rk / 1e6 / peak}
+                     "clb_rk438_particle_steps_per_s": ntot / rk * 1e3, "clb_rk438_hbm_frac": 168 * nloc / rk / 1e6 / peak,
+                     "bound_note": "the LB/CLB right-hand sides move 24/32 B per particle through three passes that are "
+                                   "co-limited by the shared-memory data pipe (lane-private v-deposit: 18 wavefronts per warp "
+                                   "of particles) and instruction issue, see profiles/README.md"}
         vs.close()
 
     cpu = None
     if world == 1 and rank == 0 and not args.no_cpu:
+        p.close()                                  # the CPU leg needs the host's memory bandwidth, not the GPU's
         try:
-            cpu = cpu_baseline()
+            cpu = cpu_baseline(ntot)
         except Exception as exc:   # the CPU leg must never take the GPU number down with it
             cpu = {"error": repr(exc)}
 
@@ -392,7 +563,8 @@ def run_gpu(args):
             "metric": "particle-steps/sec", "value": value, "unit": "particle-steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
-            "roofline": roofline, "deposit": deposit, "secondary": secondary, "cpu_baseline": cpu, "e2e": e2e,
+            "roofline": roofline, "general_weights": general, "deposit": deposit, "secondary": secondary,
+            "cpu_baseline": cpu, "e2e": e2e, "parity": parity, "timing": timing, "ceilings": ceil,
             "gpu_launches": int(launches), "clocks": clocks,
             "step_hbm_frac": ALG_BYTES_PER_PARTICLE * nloc * args.steps / (ms * 1e-3) / 1e9 / peak,
         }))
@@ -425,8 +597,12 @@ def main():
     ap.add_argument("--no-peer", action="store_true", help="NCCL all-reduce instead of the fused NVLink peer-memory exchange (A/B)")
     ap.add_argument("--no-pdl", action="store_true", help="disable programmatic dependent launch of the pass kernels (A/B)")
     ap.add_argument("--no-fuse", action="store_true", help="separate reduce/solve kernels instead of the last-CTA finish (A/B)")
+    ap.add_argument("--repeats", type=int, default=5, help="timed regions of K steps each; the median is reported")
+    ap.add_argument("--no-parity", action="store_true", help="skip the small sharded run checked against the CPU oracle")
+    ap.add_argument("--no-ceilings", action="store_true", help="skip tools/microbench/peaks")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    args.repeats = max(args.repeats, 1)
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define VM_ABI_VERSION 1
+#define VM_ABI_VERSION 2
 
 typedef struct vm_ctx vm_ctx;
 typedef struct vm_particles vm_particles;
@@ -118,6 +118,10 @@ int vm_particles_download_aos(vm_particles* p, double* z3xn);
 int vm_particles_upload_soa(vm_particles* p, const double* x, const double* v, const double* w);
 int vm_particles_download_soa(vm_particles* p, double* x, double* v, double* w);
 int vm_particles_copy(vm_particles* dst, vm_particles* src);
+/* Every sampler of the reference gives all particles ONE weight (w = 1/N: src/examples/normal.jl:33, w = L/N:
+ * bumpontail.jl:70).  A host that knows this declares it instead of uploading the weight row: the device array is
+ * filled at HBM rate (no 8 B/particle over PCIe) and the passes take w0 as a kernel parameter. */
+int vm_particles_set_uniform_weight(vm_particles* p, double w0);
 
 /* Asynchronous, decimated snapshots for the driver loops (run!(::SplittingMethod) writes the full state
  * after every step, src/methods/splitting.jl:42 -- 1.6 GB per step at 1e8 particles).
@@ -230,6 +234,29 @@ typedef enum vm_run_flags {
 int vm_vp_run(vm_field* f, vm_particles* p, double dt, int nsteps, int diag_every, int flags,
               double chi, double* diag_host);
 
+/* integrate_vp! (src/vlasov_poisson.jl:94-115) driven by an ExternalField (src/electric_field.jl:55-77): no
+ * deposit, no solve -- at step `it` the coefficients are column round(it*dt / coeff_dt) of the prescribed history
+ * coeffs_host (column-major n_basis x ncols: the memory of the Julia matrix `coeffs`, time index 0 first), and
+ * x += dt*chi/2 v ; v += dt*chi E(x)/chi^2 ; x += dt*chi/2 v.  The history is uploaded once and stays on the
+ * device for the call; on return the field holds the last column used (poisson.phi of the reference).
+ * Diagnostics rows [W, K, M, sum_w] as vm_vp_run, W = energy(::ExternalField) of the column in use (:75). */
+int vm_vp_run_external(vm_field* f, vm_particles* p, double dt, int nsteps, int diag_every, double chi,
+                       const double* coeffs_host, int ncols, double coeff_dt, double* diag_host);
+
+typedef enum vm_vf_flags {
+    VM_VF_KEEP_POTENTIAL = 1  /* do not re-deposit / re-solve: evaluate with the field's current coefficients */
+} vm_vf_flags;
+/* lorentz_force!(zdot, t, z, params) (src/models/vlasov_poisson.jl:23-29), and with VM_VF_KEEP_POTENTIAL the
+ * second halves of v_advection! / v_acceleration! (:36-50): update_potential!(model) from the particle state,
+ * then xdot = v, vdot = -phi'(x).  The result stays on the device (vdot in the handle's work array, read by
+ * vm_vp_rk_run; xdot IS the v array); either host pointer may be NULL -- nothing is then copied. */
+int vm_vp_vector_field(vm_field* f, vm_particles* p, int flags, double* xdot_host, double* vdot_host);
+
+/* nsteps classical RK4 steps of zdot = lorentz_force(z) with everything on the device: the unsplit vector field
+ * (src/models/vlasov_poisson.jl:23-29) driven the way a generic explicit Runge-Kutta integrator of
+ * GeometricIntegrators would drive it -- four update_potential! + gather evaluations per step. */
+int vm_vp_rk4_run(vm_field* f, vm_particles* p, double dt, int nsteps);
+
 /* [W, K, M, sum_w] for the current state (deposit + solve + reductions). */
 int vm_diagnostics(vm_field* f, vm_particles* p, double chi, double* out4);
 
@@ -249,6 +276,12 @@ int vm_vspline_get_mass_matrix(vm_vspline* s, double* host_nv_x_nv);  /* galerki
 /* projection(v, dist, sdist): src/projections/distribution.jl:35-55.
  * Uses the particles' v and w arrays. */
 int vm_vproject(vm_vspline* s, vm_particles* p);
+/* The same with replacement velocities `v_host` (length N) instead of the particles' own: the `velocities`
+ * argument of projection(velocities, dist, sdist) when a user-side integrator passes stage values.  The device
+ * particle state is NOT modified (the values live in a scratch array for the call). */
+int vm_vproject_at(vm_vspline* s, vm_particles* p, const double* v_host);
+int vm_vmoments_at(vm_vspline* s, vm_particles* p, const double* v_host, double* out5, double* A2);
+int vm_lb_rhs_at(vm_vspline* s, vm_particles* p, const double* v_host, double nu, int conservative, double* vdot_host);
 /* spline.(v), (Derivative(1)*spline).(v) at host points (either output may be NULL). */
 int vm_vspline_eval(vm_vspline* s, const double* v_host, long n, double* f_host, double* df_host);
 /* compute_f_densities / compute_df_densities (src/projections/density.jl:6-20):

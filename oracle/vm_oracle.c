@@ -378,6 +378,81 @@ void vmo_integrate_vp(double* x, double* v, const double* w, long np, double dt,
     free(rhs); free(phi); free(acc);
 }
 
+/* integrate_vp! driven by an ExternalField: update!(f, x, w, t) sets ts = round(t / dt_c) and
+ * phi = coeffs[:, ts] (src/electric_field.jl:66-69; no deposit, no solve), efield! gathers, ScaledField divides
+ * by chi^2 (:26-29); loop body src/vlasov_poisson.jl:94-115.  coeffs is column-major n x ncols (time index 0
+ * first, as the OffsetMatrix of :62).  diag rows [W, K, M] with W = energy(::ExternalField) (:75) / chi^2. */
+void vmo_integrate_vp_external(double* x, double* v, const double* w, long np, double dt, double chi,
+                               int nt, int nsave, double a, double b, int n, int k, int shift,
+                               const double* S, const double* coeffs, int ncols, double dt_c, double* diag)
+{
+    double Dt = dt * chi;
+    double* acc = (double*)malloc(sizeof(double) * (size_t)np);
+    int ts = 0, row = 0;
+    (void)ncols;
+    for (int it = 0; it <= nt; ++it) {
+        const double t = it * dt;
+        if (it > 0) {
+            for (long p = 0; p < np; ++p) x[p] += 0.5 * Dt * v[p];
+            ts = (int)nearbyint(t / dt_c);                      /* Julia round(): ties to even */
+            vmo_eval_dphi(x, np, a, b, n, k, shift, coeffs + (size_t)n * ts, acc);
+            for (long p = 0; p < np; ++p) acc[p] = -acc[p] / (chi * chi);
+            for (long p = 0; p < np; ++p) v[p] += Dt * acc[p];
+            for (long p = 0; p < np; ++p) x[p] += 0.5 * Dt * v[p];
+        }
+        if (nsave > 0 && it % nsave == 0) {
+            ld K = 0, M = 0;
+            ts = (int)nearbyint(t / dt_c);
+            for (long p = 0; p < np; ++p) { K += (ld)w[p] * v[p] * v[p]; M += (ld)w[p] * v[p]; }
+            diag[3 * row + 0] = vmo_field_energy(S, n, coeffs + (size_t)n * ts) / (chi * chi);
+            diag[3 * row + 1] = (double)(0.5L * K);
+            diag[3 * row + 2] = (double)M;
+            ++row;
+        }
+    }
+    free(acc);
+}
+
+/* lorentz_force!(zdot, t, z, params) (src/models/vlasov_poisson.jl:23-29): update_potential!(model) -- deposit
+ * from x_src (NULL: the state itself, i.e. the self-consistent reading) and solve -- then
+ * zdot[1,i] = z[2,i], zdot[2,i] = -phi(z[1,i], Derivative(1)). */
+void vmo_lorentz_force(const double* x, const double* v, const double* w, long np, double a, double b,
+                       int n, int k, int shift, const double* S, const double* x_src,
+                       double* xdot, double* vdot)
+{
+    double* rhs = (double*)malloc(sizeof(double) * n);
+    double* phi = (double*)malloc(sizeof(double) * n);
+    vmo_deposit_periodic(x_src ? x_src : x, w, np, a, b, n, k, shift, rhs);
+    vmo_poisson_solve(S, n, rhs, phi);
+    vmo_eval_dphi(x, np, a, b, n, k, shift, phi, vdot);
+    for (long p = 0; p < np; ++p) { xdot[p] = v[p]; vdot[p] = -vdot[p]; }
+    free(rhs); free(phi);
+}
+
+/* One classical RK4 step of zdot = lorentz_force(z): what a generic (unsplit) Runge-Kutta driver of
+ * GeometricIntegrators does with the vector field above.  Stage sums in the textbook order. */
+void vmo_vp_rk4_step(double* x, double* v, const double* w, long np, double dt, double a, double b,
+                     int n, int k, int shift, const double* S)
+{
+    size_t N = (size_t)np;
+    double* buf = (double*)malloc(sizeof(double) * N * 10);
+    double *xs = buf, *vs = buf + N, *kx[4], *kv[4];
+    const double c[4] = {0.0, 0.5, 0.5, 1.0};
+    for (int s = 0; s < 4; ++s) { kx[s] = buf + (2 + 2 * s) * N; kv[s] = buf + (3 + 2 * s) * N; }
+    for (int s = 0; s < 4; ++s) {
+        for (size_t p = 0; p < N; ++p) {
+            xs[p] = s ? x[p] + (c[s] * dt) * kx[s - 1][p] : x[p];
+            vs[p] = s ? v[p] + (c[s] * dt) * kv[s - 1][p] : v[p];
+        }
+        vmo_lorentz_force(xs, vs, w, np, a, b, n, k, shift, S, NULL, kx[s], kv[s]);
+    }
+    for (size_t p = 0; p < N; ++p) {
+        x[p] += (dt / 6.0) * (kx[0][p] + 2.0 * kx[1][p] + 2.0 * kx[2][p] + kx[3][p]);
+        v[p] += (dt / 6.0) * (kv[0][p] + 2.0 * kv[1][p] + 2.0 * kv[2][p] + kv[3][p]);
+    }
+    free(buf);
+}
+
 /* ====================================================================== */
 /* v-space: projection, moments, LB / CLB right-hand sides, RK438         */
 /* ====================================================================== */

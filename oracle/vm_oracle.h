@@ -103,6 +103,17 @@ void vmo_integrate_vp(double* x, double* v, const double* w, long np, double dt,
                       int nt, int nsave, double a, double b, int n, int k, int shift,
                       const double* S, double* diag, double* phi_hist);
 
+/* integrate_vp! with an ExternalField (src/electric_field.jl:55-77, src/vlasov_poisson.jl:94-115) */
+void vmo_integrate_vp_external(double* x, double* v, const double* w, long np, double dt, double chi,
+                               int nt, int nsave, double a, double b, int n, int k, int shift,
+                               const double* S, const double* coeffs, int ncols, double dt_c, double* diag);
+/* lorentz_force! (src/models/vlasov_poisson.jl:23-29) and one RK4 step of it */
+void vmo_lorentz_force(const double* x, const double* v, const double* w, long np, double a, double b,
+                       int n, int k, int shift, const double* S, const double* x_src,
+                       double* xdot, double* vdot);
+void vmo_vp_rk4_step(double* x, double* v, const double* w, long np, double dt, double a, double b,
+                     int n, int k, int shift, const double* S);
+
 /* ------------------------------------------- v-space (Lenard-Bernstein) --- */
 /* projection(v, dist, sdist): src/projections/distribution.jl:35-55.
  * coef[nv] = M^{-1} (sum_p w_p phi_i(v_p)); also returns the raw rhs if

@@ -54,6 +54,9 @@ def _sig(lib):
     lib.vmo_s_acceleration.argtypes = [_p, _p, _p, _l, _d, _d, _d, _i, _i, _i, _p, _p]
     lib.vmo_vp_strang_step.argtypes = [_p, _p, _p, _l, _d, _d, _d, _i, _i, _i, _p, _p]
     lib.vmo_integrate_vp.argtypes = [_p, _p, _p, _l, _d, _d, _i, _i, _d, _d, _i, _i, _i, _p, _p, _p]
+    lib.vmo_integrate_vp_external.argtypes = [_p, _p, _p, _l, _d, _d, _i, _i, _d, _d, _i, _i, _i, _p, _p, _i, _d, _p]
+    lib.vmo_lorentz_force.argtypes = [_p, _p, _p, _l, _d, _d, _i, _i, _i, _p, _p, _p, _p]
+    lib.vmo_vp_rk4_step.argtypes = [_p, _p, _p, _l, _d, _d, _d, _i, _i, _i, _p]
     lib.vmo_vproject.argtypes = [_p, _p, _l, _d, _d, _i, _i, _p, _p, _p]
     lib.vmo_vspline_eval.argtypes = [_p, _l, _d, _d, _i, _i, _p, _p, _p]
     lib.vmo_vmoments.argtypes = [_p, _l, _d, _d, _i, _i, _p, _p]
@@ -182,6 +185,27 @@ def integrate_vp(x, v, w, dt, chi, nt, nsave, a, b, n, k, shift, S, want_phi=Fal
     lib().vmo_integrate_vp(_ptr(x), _ptr(v), _ptr(w), x.size, dt, chi, nt, nsave, a, b, n, k, shift,
                            _ptr(S), _ptr(diag), _ptr(phi_hist) if want_phi else None)
     return (diag, phi_hist) if want_phi else diag
+
+
+def integrate_vp_external(x, v, w, dt, chi, nt, nsave, a, b, n, k, shift, S, coeffs, dt_c):
+    """Legacy loop in a prescribed field; coeffs is (n, ncols), column ts = phi at time ts * dt_c.  In-place on x, v."""
+    cm = np.asfortranarray(np.asarray(coeffs, dtype=np.float64))
+    nrec = (nt // nsave + 1) if nsave > 0 else 0
+    diag = np.zeros((max(nrec, 1), 3))
+    lib().vmo_integrate_vp_external(_ptr(x), _ptr(v), _ptr(w), x.size, dt, chi, nt, nsave, a, b, n, k, shift,
+                                    _ptr(S), cm.ctypes.data_as(_p), cm.shape[1], dt_c, _ptr(diag))
+    return diag[:nrec]
+
+
+def lorentz_force(x, v, w, a, b, n, k, shift, S, x_src=None):
+    xdot, vdot = np.empty_like(x), np.empty_like(x)
+    lib().vmo_lorentz_force(_ptr(x), _ptr(v), _ptr(w), x.size, a, b, n, k, shift, _ptr(S),
+                            _ptr(x_src) if x_src is not None else None, _ptr(xdot), _ptr(vdot))
+    return xdot, vdot
+
+
+def vp_rk4_step(x, v, w, dt, a, b, n, k, shift, S):
+    lib().vmo_vp_rk4_step(_ptr(x), _ptr(v), _ptr(w), x.size, dt, a, b, n, k, shift, _ptr(S))
 
 
 # ---------------------------------------------------------------- v-space ---

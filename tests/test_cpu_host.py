@@ -21,7 +21,7 @@ def test_library_exports_every_declared_symbol(vm):
     for name in sorted(declared):
         assert hasattr(lib, name), f"libvlasov_b200.so does not export {name}"
     assert set(vm._lib.SIGNATURES) == declared
-    assert lib.vm_abi_version() == 1
+    assert lib.vm_abi_version() == 2
 
 
 def test_no_cpu_fallback(vm):

@@ -23,24 +23,51 @@ rank, world = dist.get_rank(), dist.get_world_size()
 ctx = vm.init_distributed_context()
 assert ctx.comm_info() == (rank, world)
 rng = np.random.default_rng(5)
-n, k, npart, dt, nt = 32, 4, 40001, 0.1, 6
+k, npart, dt, nt = 4, 40001, 0.1, 6
 a, b = 0.0, 2 * np.pi / 0.3
 x = rng.uniform(a, b, npart); v = rng.standard_normal(npart); w = np.full(npart, (b - a) / npart)
 lo, hi = vm.shard_bounds(npart, rank, world)
-fld = vm.DeviceField(ctx, a, b, k, n, 0)
 p = vm.DeviceParticles(ctx, hi - lo)
-p.upload(x[lo:hi], v[lo:hi], w[lo:hi])
-diag = fld.run(p, dt, nt, 2, 0, 1.0)
-xg, vg, _ = p.download(w=False)
+for n in (32, 200, 1024):          # one-level fused finish, two-level finish (+ separate solve kernel) at 200 and 1024 cells
+    fld = vm.DeviceField(ctx, a, b, k, n, 0)
+    p.upload(x[lo:hi], v[lo:hi], w[lo:hi])
+    diag = fld.run(p, dt, nt, 2, 0, 1.0)
+    xg, vg, _ = p.download(w=False)
+    S = orc.periodic_stiffness(a, b, n, k, 0)
+    xo, vo = x.copy(), v.copy()
+    dref, phiref = orc.integrate_vp(xo, vo, w, dt, 1.0, nt, 2, a, b, n, k, 0, S, want_phi=True)
+    assert np.max(np.abs(xg - xo[lo:hi])) <= 1e-11 and np.max(np.abs(vg - vo[lo:hi])) <= 1e-11, n
+    assert np.allclose(diag[:, :3], dref, rtol=1e-10, atol=1e-13), n
+    phi = torch.from_numpy(fld.coefficients.copy()); ref = phi.clone(); dist.broadcast(ref, src=0)
+    assert torch.equal(phi, ref), "field coefficients differ between ranks"
+    assert np.max(np.abs(phi.numpy() - phiref[-1])) <= 1e-10 * np.max(np.abs(phiref[-1]))
+    # update!(potential) is idempotent: a second (and third) solve without a fresh deposit leaves phi alone,
+    # whether rhs came out of the fused exchange, the NCCL all-reduce or a plain vm_deposit
+    fld.solve(); phi_b = fld.coefficients.copy(); fld.solve()
+    assert np.array_equal(fld.coefficients, phi_b), ("repeated solve changed phi", n)
+    # (the in-kernel solve of the fused pass and the stand-alone solve kernel sum in different orders: rounding only)
+    assert np.max(np.abs(phi_b - phi.numpy())) <= 1e-13 * np.max(np.abs(phi_b)), ("solve after the run rescaled phi", n)
+    fld.deposit(p, 0); fld.solve(); phi2 = fld.coefficients.copy(); fld.solve()
+    assert np.array_equal(fld.coefficients, phi2)
+    rhs_all = orc.deposit_periodic(xo, w, a, b, n, k, 0)
+    assert np.max(np.abs(phi2 - orc.poisson_solve(S, rhs_all))) <= 1e-10 * np.max(np.abs(phi2))
+    fld.close()
+# a rank with an EMPTY shard takes part in every exchange (one particle over `world` ranks)
+n = 16
+small = 1
+lo2, hi2 = vm.shard_bounds(small, rank, world)
+q = vm.DeviceParticles(ctx, hi2 - lo2)
+q.upload(x[lo2:hi2], v[lo2:hi2], w[lo2:hi2])
+fld = vm.DeviceField(ctx, a, b, k, n, 0)
+diag = fld.run(q, dt, 4, 2, 0, 1.0)
 S = orc.periodic_stiffness(a, b, n, k, 0)
-xo, vo = x.copy(), v.copy()
-dref, phiref = orc.integrate_vp(xo, vo, w, dt, 1.0, nt, 2, a, b, n, k, 0, S, want_phi=True)
-assert np.max(np.abs(xg - xo[lo:hi])) <= 1e-11 and np.max(np.abs(vg - vo[lo:hi])) <= 1e-11
-assert np.allclose(diag[:, :3], dref, rtol=1e-10, atol=1e-13)
-phi = torch.from_numpy(fld.coefficients.copy()); ref = phi.clone(); dist.broadcast(ref, src=0)
-assert torch.equal(phi, ref), "field coefficients differ between ranks"
-assert np.max(np.abs(phi.numpy() - phiref[-1])) <= 1e-10 * np.max(np.abs(phiref[-1]))
-# v-space: sharded CLB right-hand side
+xo, vo = x[:small].copy(), v[:small].copy()
+dref = orc.integrate_vp(xo, vo, w[:small].copy(), dt, 1.0, 4, 2, a, b, n, k, 0, S)
+assert np.allclose(diag[:, :3], dref, rtol=1e-10, atol=1e-15), "diagnostics with empty shards"
+xg = q.download(w=False)[0]
+assert np.max(np.abs(xg - xo[lo2:hi2]), initial=0.0) <= 1e-12
+fld.close()
+# v-space: sharded CLB right-hand side and a fused RK438 run (projection + moments exchanged in-kernel)
 vs = vm.DeviceVSpline(ctx, -10.0, 10.0, 41, 4, 1)
 wv = np.full(npart, 1.0 / npart)
 p.upload(v=v[lo:hi], w=wv[lo:hi])
@@ -48,6 +75,14 @@ vdot = vs.lb_rhs(p, 1.0, True)
 M = orc.dirichlet_mass(-10.0, 10.0, 41, 4)
 vref, _, _ = orc.lb_rhs(v, wv, -10.0, 10.0, 41, 4, M, 1.0, True)
 assert np.max(np.abs(vdot - vref[lo:hi])) <= 1e-10 * np.max(np.abs(vref))
+d = vs.rk438_run(p, 1e-2, 3, 1.0, True, 1)
+vo = v.copy()
+for _ in range(3):
+    orc.lb_rk438_step(vo, wv, 1e-2, -10.0, 10.0, 41, 4, M, 1.0, True)
+assert np.max(np.abs(p.download(x=False, w=False)[1] - vo[lo:hi])) <= 1e-11
+assert abs(d[-1, 1] - vo.sum()) <= 1e-9 * npart
+c = torch.from_numpy(vs.coefficients.copy()); ref = c.clone(); dist.broadcast(ref, src=0)
+assert torch.equal(c, ref), "v-space coefficients differ between ranks"
 dist.barrier()
 print("ok", rank)
 """

@@ -47,6 +47,7 @@ SIGNATURES = {
     "vm_particles_upload_soa": (_i, [_vp, _dp, _dp, _dp]),
     "vm_particles_download_soa": (_i, [_vp, _dp, _dp, _dp]),
     "vm_particles_copy": (_i, [_vp, _vp]),
+    "vm_particles_set_uniform_weight": (_i, [_vp, _d]),
     "vm_particles_snapshot_begin": (_i, [_vp, _dp, _dp]),
     "vm_particles_snapshot_wait": (_i, [_vp]),
     "vm_host_alloc": (_i, [C.c_size_t, C.POINTER(_vp)]),
@@ -67,6 +68,9 @@ SIGNATURES = {
     "vm_vp_drift": (_i, [_vp, _d]),
     "vm_vp_kick": (_i, [_vp, _vp, _d, _d]),
     "vm_vp_run": (_i, [_vp, _vp, _d, _i, _i, _i, _d, _dp]),
+    "vm_vp_run_external": (_i, [_vp, _vp, _d, _i, _i, _d, _dp, _i, _d, _dp]),
+    "vm_vp_vector_field": (_i, [_vp, _vp, _i, _dp, _dp]),
+    "vm_vp_rk4_run": (_i, [_vp, _vp, _d, _i]),
     "vm_diagnostics": (_i, [_vp, _vp, _d, _dp]),
     "vm_vspline_create": (_i, [_vp, _d, _d, _i, _i, _i, C.POINTER(_vp)]),
     "vm_vspline_destroy": (_i, [_vp]),
@@ -76,6 +80,9 @@ SIGNATURES = {
     "vm_vspline_get_rhs": (_i, [_vp, _dp]),
     "vm_vspline_get_mass_matrix": (_i, [_vp, _dp]),
     "vm_vproject": (_i, [_vp, _vp]),
+    "vm_vproject_at": (_i, [_vp, _vp, _dp]),
+    "vm_vmoments_at": (_i, [_vp, _vp, _dp, _dp, _dp]),
+    "vm_lb_rhs_at": (_i, [_vp, _vp, _dp, _d, _i, _dp]),
     "vm_vspline_eval": (_i, [_vp, _dp, _l, _dp, _dp]),
     "vm_vmoments": (_i, [_vp, _vp, _dp, _dp]),
     "vm_lb_rhs": (_i, [_vp, _vp, _d, _i, _dp]),
@@ -85,6 +92,7 @@ SIGNATURES = {
 # enums of the header
 VM_DEPOSIT_DETERMINISTIC, VM_DEPOSIT_ATOMIC = 0, 1
 VM_RUN_SPLIT_KICK, VM_RUN_FROZEN_FIELD, VM_RUN_ATOMIC_DEPOSIT, VM_RUN_UNFUSED = 1, 2, 4, 8
+VM_VF_KEEP_POTENTIAL = 1
 (VM_FILL_NORMAL, VM_FILL_BUMP_ON_TAIL, VM_FILL_DOUBLE_MAXWELLIAN, VM_FILL_UNIFORM,
  VM_FILL_SHIFTED_NORMAL_V, VM_FILL_SHIFTED_UNIFORM, VM_FILL_LANDAU) = range(7)
 VM_OK, VM_ERR_INVALID, VM_ERR_CUDA, VM_ERR_NOMEM, VM_ERR_NCCL, VM_ERR_UNSUPPORTED, VM_ERR_NO_DEVICE = range(7)   # vm_status
@@ -132,7 +140,7 @@ def lib():
             fn = getattr(handle, name)       # AttributeError if the ABI lost a symbol
             fn.restype = res
             fn.argtypes = args
-        if handle.vm_abi_version() != 1:
+        if handle.vm_abi_version() != 2:
             raise RuntimeError("libvlasov_b200.so ABI version mismatch")
         _lib = handle
     return _lib

@@ -291,28 +291,37 @@ class CollisionEntropy:
 def projection(velocities, dist: ParticleDistribution, final_dist: SplineDistribution):
     """projection(v, dist, sdist) (src/projections/distribution.jl:35-55): deposit + mass solve.
 
-    `velocities` is None (use the distribution's device state) or a host vector that replaces it."""
+    `velocities` is None (use the distribution's device state) or a host vector used instead of it; like the
+    reference, a replacement vector only feeds the projection -- dist.particles (host and device) stay untouched."""
     dev = dist.device()
     if velocities is not None:
-        dev.upload(v=np.asarray(velocities, dtype=np.float64).reshape(-1))
-    final_dist.vs.project(dev)
+        final_dist.vs.project_at(dev, np.asarray(velocities, dtype=np.float64).reshape(-1))
+    else:
+        final_dist.vs.project(dev)
     return final_dist.spline
 
 
-def compute_f_densities(distribution: SplineDistribution, dist: ParticleDistribution):
-    """(n, n u, n eps) = unweighted particle sums of f_s, v f_s, v^2 f_s (density.jl:6-13)."""
-    m5, _ = distribution.vs.moments(dist.device())
+def _moments(distribution: SplineDistribution, dist: ParticleDistribution, v=None):
+    if v is None:
+        return distribution.vs.moments(dist.device())
+    return distribution.vs.moments_at(dist.device(), np.asarray(v, dtype=np.float64).reshape(-1))
+
+
+def compute_f_densities(distribution: SplineDistribution, dist: ParticleDistribution, v=None):
+    """(n, n u, n eps) = unweighted particle sums of f_s, v f_s, v^2 f_s (density.jl:6-13); v: the `vp` argument
+    of the reference (default: the distribution's own velocities)."""
+    m5, _ = _moments(distribution, dist, v)
     return m5[0], m5[1], m5[2]
 
 
-def compute_df_densities(distribution: SplineDistribution, dist: ParticleDistribution):
-    m5, _ = distribution.vs.moments(dist.device())
+def compute_df_densities(distribution: SplineDistribution, dist: ParticleDistribution, v=None):
+    m5, _ = _moments(distribution, dist, v)
     return m5[3], m5[4]
 
 
-def compute_coefficients(distribution: SplineDistribution, particle_dist: ParticleDistribution):
+def compute_coefficients(distribution: SplineDistribution, particle_dist: ParticleDistribution, v=None):
     """A1, A2 (lenard_bernstein_conservative.jl:11-21)."""
-    _, A = distribution.vs.moments(particle_dist.device())
+    _, A = _moments(distribution, particle_dist, v)
     return A[0], A[1]
 
 
@@ -340,13 +349,11 @@ def s_acceleration_(model: VlasovPoisson, dt: float):
     model.potential.field.kick(model.distribution.device(), dt, -1.0)
 
 
-def lorentz_force_(model: VlasovPoisson):
+def lorentz_force_(model: VlasovPoisson, *, to_host: bool = True):
     """lorentz_force! (:23-29): (xdot, vdot) = (v, -phi'(x)) with the potential refreshed from the state.
-    Returns host arrays (xdot, vdot) for generic (unsplit) Runge-Kutta drivers."""
-    update_potential_(model)
-    dev = model.distribution.device()
-    vdot = model.potential.field.gather_E(dev, 1.0)
-    return dev.download(x=False, w=False)[1], vdot
+    One C-ABI call (vm_vp_vector_field); to_host=False keeps both on the device (vdot in the handle's work array,
+    xdot is the v array) and returns (None, None) -- at 1e8 particles the host round trip is 1.6 GB per call."""
+    return model.potential.field.vector_field(model.distribution.device(), False, to_host)
 
 
 def v_advection_(model: VlasovPoisson):
@@ -376,8 +383,8 @@ def LB_rhs_(model: LenardBernstein, v=None):
     """LB_rhs! / CLB_rhs! (lenard_bernstein.jl:20-30, lenard_bernstein_conservative.jl:24-36):
     vdot for the model's particles (optionally with replacement velocities v)."""
     dev = model.dist.device()
-    if v is not None:
-        dev.upload(v=np.asarray(v, dtype=np.float64).reshape(-1))
+    if v is not None:      # stage values of a user-side integrator: the particle state is not modified
+        return model.ent.dist.vs.lb_rhs_at(dev, np.asarray(v, dtype=np.float64).reshape(-1), model.ν, model.conservative)
     return model.ent.dist.vs.lb_rhs(dev, model.ν, model.conservative)
 
 
@@ -427,6 +434,9 @@ def run_(method, h5file: Optional[str] = None, *, save_every: int = 0, diag_ever
     reference's dataset names: z[nd, np, nt] (and t[nt]).
     Returns the model's distribution with the final state copied back (splitting.jl:49)."""
     nt = _ntime(method.tspan, method.tstep)
+    if diag_every > 0 and save_every > 0 and save_every % diag_every != 0:
+        # every chunk of save_every steps then starts on a diagnostics step, so the cadence continues across chunks
+        raise ValueError("save_every must be a multiple of diag_every")
     if isinstance(method, SplittingMethod):
         return _run_splitting(method, nt, h5file, save_every, diag_every)
     if isinstance(method, GeometricIntegrator):
@@ -488,11 +498,13 @@ def _run_splitting(method: SplittingMethod, nt, h5file, save_every, diag_every):
     if keep:
         snaps.begin()
     done = 0
+    dtimes = []
     for n in chunks:
-        de = diag_every if (diag_every > 0 and n % diag_every == 0) else 0
-        d = pot.field.run(dev, method.tstep, n, de, flags, 1.0)     # enqueued; overlaps the pending snapshot copy
-        if d is not None:
+        d = pot.field.run(dev, method.tstep, n, diag_every, flags, 1.0)     # enqueued; overlaps the pending snapshot copy
+        if d is not None:                      # rows at steps done, done + diag_every, ... (row 0 repeats the previous chunk's last)
+            tt = method.tspan[0] + (done + diag_every * np.arange(d.shape[0])) * method.tstep
             diags.append(d if not diags else d[1:])
+            dtimes.append(tt if not dtimes else tt[1:])
         done += n
         times.append(method.tspan[0] + done * method.tstep)
         if keep:
@@ -500,7 +512,8 @@ def _run_splitting(method: SplittingMethod, nt, h5file, save_every, diag_every):
             snaps.begin()
     if keep:
         snaps.finish()
-    method.diagnostics = np.concatenate(diags) if diags else None
+    method.diagnostics = np.concatenate(diags) if diags else None            # rows [W, K, M, sum_w]
+    method.diagnostics_t = np.concatenate(dtimes) if dtimes else None
     if h5file is not None:
         np.savez(h5file, z=snaps.z, t=np.asarray(times))
     if dist.particles.data is not None:
@@ -520,8 +533,7 @@ def _run_rk438(method: GeometricIntegrator, nt, h5file, save_every, diag_every):
         snaps.begin()
     done = 0
     for n in chunks:
-        de = diag_every if (diag_every > 0 and n % diag_every == 0) else 0
-        d = vs.rk438_run(dev, method.tstep, n, model.ν, model.conservative, de)
+        d = vs.rk438_run(dev, method.tstep, n, model.ν, model.conservative, diag_every)
         if d is not None:
             d = d.copy(); d[:, 0] += method.tspan[0] + done * method.tstep
             diags.append(d if not diags else d[1:])

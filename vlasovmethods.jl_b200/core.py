@@ -210,6 +210,10 @@ class DeviceParticles:
     def snapshot_wait(self):
         L.check(L.lib().vm_particles_snapshot_wait(self._h), self.ctx._h)
 
+    def set_uniform_weight(self, w0: float):
+        """Declare w_p = w0 for every particle (what every sampler of the reference produces) instead of uploading w."""
+        L.check(L.lib().vm_particles_set_uniform_weight(self._h, float(w0)), self.ctx._h)
+
     def copy_from(self, other: "DeviceParticles"):
         L.check(L.lib().vm_particles_copy(self._h, other._h), self.ctx._h)
 
@@ -313,6 +317,31 @@ class DeviceField:
                                   L.dptr(diag)), self.ctx._h)
         return diag
 
+    def run_external(self, p: DeviceParticles, dt: float, nsteps: int, coeffs, coeff_dt: float, diag_every: int = 0,
+                     chi: float = 1.0):
+        """nsteps leapfrog steps in a prescribed field: coeffs is (n_basis, ncols), column ts = phi at time ts*coeff_dt
+        (ExternalField, src/electric_field.jl:55-77).  Returns diag rows [W, K, M, sum_w] (or None)."""
+        coeffs = np.asarray(coeffs, dtype=np.float64)
+        if coeffs.ndim != 2 or coeffs.shape[0] != self.n:
+            raise ValueError(f"coeffs must be ({self.n}, ncols)")
+        cm = np.asfortranarray(coeffs)                  # column-major: the memory of the Julia matrix
+        diag = np.zeros((nsteps // diag_every + 1, 4)) if diag_every > 0 else None
+        L.check(L.lib().vm_vp_run_external(self._h, p._h, float(dt), int(nsteps), int(diag_every), float(chi),
+                                           cm.ctypes.data_as(L._dp), int(cm.shape[1]), float(coeff_dt), L.dptr(diag)), self.ctx._h)
+        return diag
+
+    def vector_field(self, p: DeviceParticles, keep_potential: bool = False, to_host: bool = True):
+        """lorentz_force!: (xdot, vdot) = (v, -phi'(x)) after update_potential!; to_host=False leaves them on the device."""
+        xdot = np.empty(p.n) if to_host else None
+        vdot = np.empty(p.n) if to_host else None
+        L.check(L.lib().vm_vp_vector_field(self._h, p._h, L.VM_VF_KEEP_POTENTIAL if keep_potential else 0,
+                                           L.dptr(xdot), L.dptr(vdot)), self.ctx._h)
+        return xdot, vdot
+
+    def rk4_run(self, p: DeviceParticles, dt: float, nsteps: int):
+        """nsteps classical RK4 steps of the unsplit vector field lorentz_force!, device-resident."""
+        L.check(L.lib().vm_vp_rk4_run(self._h, p._h, float(dt), int(nsteps)), self.ctx._h)
+
     def diagnostics(self, p: DeviceParticles, chi: float = 1.0):
         out = np.empty(4)
         L.check(L.lib().vm_diagnostics(self._h, p._h, float(chi), L.dptr(out)), self.ctx._h)
@@ -368,6 +397,23 @@ class DeviceVSpline:
 
     def project(self, p: DeviceParticles):
         L.check(L.lib().vm_vproject(self._h, p._h), self.ctx._h)
+
+    def project_at(self, p: DeviceParticles, v):
+        """projection with replacement velocities v (the particle state on the device is not modified)."""
+        v = _f64(v, (p.n,))
+        L.check(L.lib().vm_vproject_at(self._h, p._h, L.dptr(v)), self.ctx._h)
+
+    def moments_at(self, p: DeviceParticles, v):
+        v = _f64(v, (p.n,))
+        m5, A = np.empty(5), np.empty(2)
+        L.check(L.lib().vm_vmoments_at(self._h, p._h, L.dptr(v), L.dptr(m5), L.dptr(A)), self.ctx._h)
+        return m5, A
+
+    def lb_rhs_at(self, p: DeviceParticles, v, nu: float = 1.0, conservative: bool = False):
+        v = _f64(v, (p.n,))
+        vdot = np.empty(p.n)
+        L.check(L.lib().vm_lb_rhs_at(self._h, p._h, L.dptr(v), float(nu), int(conservative), L.dptr(vdot)), self.ctx._h)
+        return vdot
 
     def eval(self, v):
         v = _f64(np.atleast_1d(v))

@@ -191,8 +191,8 @@ int vm_ctx_create(int device, vm_ctx** out)
         VM_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
         VM_CUDA(cudaEventCreateWithFlags(&c->snap_ready, cudaEventDisableTiming));
         VM_CUDA(cudaEventCreateWithFlags(&c->snap_done, cudaEventDisableTiming));
-        VM_CUDA(cudaMalloc(&c->ticket, sizeof(unsigned)));
-        VM_CUDA(cudaMemset(c->ticket, 0, sizeof(unsigned)));
+        VM_CUDA(cudaMalloc(&c->ticket, (1 + VM_MAX_GROUPS) * sizeof(unsigned)));
+        VM_CUDA(cudaMemset(c->ticket, 0, (1 + VM_MAX_GROUPS) * sizeof(unsigned)));
         {
             std::lock_guard<std::mutex> lk(g_live_mu);
             g_live.insert(c);
@@ -326,7 +326,7 @@ int vm_ctx_peer_handle(vm_ctx* ctx, void* out64)
     VM_REQUIRE(ctx != nullptr && out64 != nullptr, "vm_ctx_peer_handle: NULL argument");
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle is 64 bytes");
     if (!ctx->inbox) {
-        const size_t bytes = (size_t)VM_XFLAG_OFF * sizeof(double) + 2 * VM_MAX_PEERS * sizeof(unsigned long long);
+        const size_t bytes = (size_t)VM_XINBOX_WORDS * sizeof(unsigned long long);
         VM_CUDA(cudaMalloc(&ctx->inbox, bytes));
         VM_CUDA(cudaMemset(ctx->inbox, 0, bytes));
         VM_CUDA(cudaMalloc(&ctx->xerr, sizeof(unsigned)));
@@ -351,7 +351,7 @@ int vm_ctx_peer_connect(vm_ctx* ctx, const void* handles)
         std::memcpy(&h, (const char*)handles + 64 * r, 64);
         void* ptr = nullptr;
         VM_CUDA(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
-        ctx->peer_inbox[r] = (double*)ptr;
+        ctx->peer_inbox[r] = (unsigned long long*)ptr;
     }
     ctx->peers_connected = true;
     VM_API_END
@@ -456,6 +456,12 @@ __global__ void __launch_bounds__(256) k_weights_uniform(const double* __restric
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
         same = same && (__double_as_longlong(w[i]) == first);
     if (!__all_sync(VM_FULL_MASK, same) && (threadIdx.x & 31) == 0) atomicExch(flag, 0);
+}
+
+__global__ void __launch_bounds__(256) k_fill_const(double* __restrict__ a, long n, double c)
+{
+    const long stride = (long)gridDim.x * blockDim.x;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) a[i] = c;
 }
 
 // Host <-> device transfers of big arrays go through a pair of pinned bounce buffers so that
@@ -564,6 +570,23 @@ int vm_particles_download_soa(vm_particles* p, double* x, double* v, double* w)
     }
     VM_CUDA(cudaStreamSynchronize(p->ctx->stream));
     vm_check_peer_error(p->ctx);
+    VM_API_END
+}
+
+int vm_particles_set_uniform_weight(vm_particles* p, double w0)
+{
+    VM_API_BEGIN(p ? p->ctx : nullptr)
+    VM_REQUIRE(p != nullptr, "vm_particles_set_uniform_weight: NULL handle");
+    vm_ctx* ctx = p->ctx;
+    if (p->n > 0) {
+        // the device array is filled too (8 B/particle written at HBM rate instead of uploaded over PCIe): passes
+        // that stream per-particle weights and downloads keep working
+        k_fill_const<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(p->w, p->n, w0);
+        VM_LAUNCHED(ctx);
+    }
+    p->uniform_w = true;
+    p->w0 = w0;
+    p->w_dirty = false;
     VM_API_END
 }
 

@@ -149,42 +149,40 @@ __device__ __forceinline__ void flush_grid(double* __restrict__ grid, double* __
 }
 
 // ------------------------------------------------ fused cross-CTA finish ----
-// The last CTA to finish (atomic ticket) sums all per-CTA rows in a fixed order and, on a single
-// GPU, also solves the periodic Poisson system -- the reduce and solve launches of a step disappear.
-// Used for n <= VM_FUSE_MAX_N; larger grids use the separate multi-CTA kernels.
+// The last CTA to finish (atomic ticket) sums all per-CTA rows in a fixed order, exchanges the result with the
+// other ranks over NVLink peer memory and (small grids) solves the periodic Poisson system / the v-space mass
+// system -- the reduce, all-reduce and solve launches of a step disappear.
+//   n <= VM_FUSE_MAX_N   one level: the last CTA of the grid reduces all rows, exchanges and solves
+//   n <= VM_X_MAX_N      two levels: the last CTA of every group of VM_GROUP_CTAS CTAs reduces its group's rows
+//                        (groups finish in parallel), the last group finisher reduces the group rows and
+//                        exchanges; the O(n^2) solve then runs as its own multi-CTA kernel (one SM would need
+//                        >= 8.5 us of fp64 issue for n = 1024)
 #define VM_FUSE_MAX_N 128
-enum { FINISH_NONE = 0, FINISH_REDUCE = 1, FINISH_REDUCE_SOLVE = 2, FINISH_EXCHANGE_SOLVE = 3, FINISH_REDUCE_VSOLVE = 4 };
+enum { FINISH_NONE = 0, FINISH_REDUCE = 1, FINISH_REDUCE_SOLVE = 2, FINISH_REDUCE_VSOLVE = 4 };
 
-__device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v)
+__device__ __forceinline__ void st_volatile_v2_u64(unsigned long long* p, unsigned long long a, unsigned long long b)
 {
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+    asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
 }
-__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p)
+__device__ __forceinline__ void ld_volatile_v2_u64(const unsigned long long* p, unsigned long long& a, unsigned long long& b)
 {
-    unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ double ld_volatile_f64(const double* p)
-{
-    double v;
-    asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
-    return v;
+    asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
 }
 
 struct FinishParams {
     int mode;
-    unsigned* ticket;       // device counter, zero on entry, reset by the last CTA
-    double* rhs;            // n: reduced deposit
+    int two_level;          // rows are reduced per group of VM_GROUP_CTAS CTAs first (n > VM_FUSE_MAX_N)
+    unsigned* ticket;       // device counters, zero on entry, reset by the last CTA: [0] grid, [1 + g] group g
+    double* rhs;            // n: reduced deposit (sum over all ranks when xchg is set)
+    double* grows;          // two_level: ceil(grid / VM_GROUP_CTAS) x n group rows
     const double* G;        // n: circulant pseudo-inverse kernel      (FINISH_REDUCE_SOLVE)
     double* phi;            // n
     double* dcoef;          // n
     double inv_h;
-    // FINISH_EXCHANGE_SOLVE: all-gather of the partial grids through NVLink peer memory
-    int nranks, rank;
-    unsigned long long seq;             // exchange number; slot set = seq & 1
-    double* inbox;                      // this rank's inbox
-    double* peer[VM_MAX_PEERS];         // every rank's inbox as mapped on this device (peer[rank] == inbox)
+    // xchg: all-gather of the partial grids through NVLink peer memory ("LL" words: data + sequence number)
+    int xchg, nranks, rank;
+    unsigned long long seq;             // exchange number (identical on all ranks); slot set = seq & 1
+    unsigned long long* peer[VM_MAX_PEERS];   // every rank's inbox as mapped on this device (peer[rank] is this rank's own)
     unsigned* err;
     // FINISH_REDUCE_VSOLVE (v-space projection): coef = Minv * rhs, then one polynomial per cell
     const double* minv;                 // nv x nv
@@ -194,83 +192,58 @@ struct FinishParams {
     int nv, off, ncell, k;
 };
 
-__device__ __forceinline__ void finish_last_cta(const FinishParams& F, const double* rows, int nrows, int n,
-                                                double* __restrict__ sm_a /* >= 3n doubles, free */,
-                                                double* __restrict__ scratch /* blockDim.x doubles */)
+// Fused collective: every rank writes its n partial sums v[0..n) into slot [set][rank] of EVERY rank's inbox with
+// plain 16-byte P2P stores over NVLink, each 8-byte word carrying 32 data bits and the 32-bit sequence number of
+// this exchange -- no fence, no separate flag, one one-way NVLink latency.  Every rank then polls its own inbox
+// until the words of all ranks carry the current sequence number and sums them in rank order: the same bits on
+// every rank.  Two slot sets: a peer can be at most one exchange ahead (it needs this rank's words for the next).
+// All threads of the CTA must call; v (shared memory) holds the global sums on return (after a __syncthreads).
+__device__ __forceinline__ void exchange_ll(const FinishParams& F, double* __restrict__ v, int n, double* __restrict__ gout)
 {
-    __shared__ int s_last;
-    __threadfence();                                   // publish this CTA's row
-    __syncthreads();
-    if (threadIdx.x == 0) s_last = (atomicAdd(F.ticket, 1u) == gridDim.x - 1u);
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
     const int T = blockDim.x, t = threadIdx.x;
-    double* r_sh = sm_a;            // rhs - mean
-    double* phi_sh = sm_a + n;
-    double* g_sh = sm_a + 2 * n + 1;   // pseudo-inverse kernel G staged in shared memory: the convolution below
-                                       // must not chase n dependent global loads (measured: 5 us of a 17 us step floor)
-    if ((F.mode == FINISH_REDUCE_SOLVE || F.mode == FINISH_EXCHANGE_SOLVE) && t < n) g_sh[t] = __ldg(F.G + t);
-    int P = 1;
-    while (2 * P * n <= T && 2 * P <= nrows) P *= 2;
-    if (t < n * P) {
-        const int i = t % n, part = t / n;
+    const int set = (int)(F.seq & 1ull);
+    const unsigned long long tag = ((F.seq % 4294967295ull) + 1ull) << 32;     // never 0: the inbox starts zeroed
+    __syncthreads();
+    for (int idx = t; idx < n * F.nranks; idx += T) {
+        const int r = idx / n, i = idx - r * n;
+        const unsigned long long bits = (unsigned long long)__double_as_longlong(v[i]);
+        st_volatile_v2_u64(F.peer[r] + (size_t)(set * VM_MAX_PEERS + F.rank) * VM_XSLOT_WORDS + 2 * i,
+                           (bits & 0xffffffffull) | tag, (bits >> 32) | tag);
+    }
+    __syncthreads();                                   // v is overwritten below
+    const unsigned long long* inbox = F.peer[F.rank] + (size_t)set * VM_MAX_PEERS * VM_XSLOT_WORDS;
+    for (int i = t; i < n; i += T) {
+        unsigned long long lo[VM_MAX_PEERS], hi[VM_MAX_PEERS];
+        const long long t0 = clock64();
+        bool ok;
+        do {                                           // all ranks' words of this element in flight together
+            ok = true;
+#pragma unroll
+            for (int r = 0; r < VM_MAX_PEERS; ++r)
+                if (r < F.nranks) ld_volatile_v2_u64(inbox + (size_t)r * VM_XSLOT_WORDS + 2 * i, lo[r], hi[r]);
+#pragma unroll
+            for (int r = 0; r < VM_MAX_PEERS; ++r)
+                if (r < F.nranks) ok = ok && ((lo[r] & 0xffffffff00000000ull) == tag) && ((hi[r] & 0xffffffff00000000ull) == tag);
+            if (!ok && clock64() - t0 > (1ll << 35)) { atomicExch(F.err, 1u); break; }   // ~17 s: give up, host reports
+        } while (!ok);
         double s = 0.0;
-        for (int r = part; r < nrows; r += 8 * P) {      // 8 independent L2 loads in flight, summed in row order
-            double vals[8];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int rr = r + u * P;
-                vals[u] = (rr < nrows) ? __ldcg(rows + (size_t)rr * n + i) : 0.0;
-            }
-#pragma unroll
-            for (int u = 0; u < 8; ++u) s += vals[u];
-        }
-        scratch[part * n + i] = s;
+        for (int r = 0; r < VM_MAX_PEERS; ++r)
+            if (r < F.nranks) s += __longlong_as_double((long long)((lo[r] & 0xffffffffull) | (hi[r] << 32)));
+        v[i] = s;
+        gout[i] = s;
     }
     __syncthreads();
-    if (t < n) {
-        double s = 0.0;
-        for (int part = 0; part < P; ++part) s += scratch[part * n + t];
-        F.rhs[t] = s;
-        r_sh[t] = s;
-    }
-    if (F.mode == FINISH_EXCHANGE_SOLVE) {
-        // Fused collective: every rank writes its partial grid into slot [set][rank] of EVERY rank's
-        // inbox (P2P stores over NVLink), publishes a release flag, waits for all peers' flags and sums
-        // the slots in rank order -- the same bits on every rank.  Two slot sets: a peer can be at most
-        // one exchange ahead (it needs this rank's flag for the next one).
-        __syncthreads();
-        const int set = (int)(F.seq & 1ull);
-        for (int idx = t; idx < n * F.nranks; idx += T) {
-            const int r = idx / n, i = idx - r * n;
-            F.peer[r][(size_t)(set * VM_MAX_PEERS + F.rank) * VM_XSLOT + i] = r_sh[i];
-        }
-        __threadfence_system();
-        __syncthreads();
-        if (t < F.nranks) {
-            st_release_sys_u64((unsigned long long*)(F.peer[t] + VM_XFLAG_OFF) + set * VM_MAX_PEERS + F.rank, F.seq);
-            const unsigned long long* flag = (const unsigned long long*)(F.inbox + VM_XFLAG_OFF) + set * VM_MAX_PEERS + t;
-            const long long t0 = clock64();
-            while (ld_acquire_sys_u64(flag) < F.seq) {
-                if (clock64() - t0 > (1ll << 35)) { atomicExch(F.err, 1u); break; }   // ~17 s: give up, host reports
-            }
-        }
-        __syncthreads();
-        if (t < n) {
-            double vals[VM_MAX_PEERS];               // all loads in flight first, then the sum in rank order
-#pragma unroll
-            for (int r = 0; r < VM_MAX_PEERS; ++r)
-                vals[r] = (r < F.nranks) ? ld_volatile_f64(F.inbox + (size_t)(set * VM_MAX_PEERS + r) * VM_XSLOT + t) : 0.0;
-            double s = 0.0;
-#pragma unroll
-            for (int r = 0; r < VM_MAX_PEERS; ++r)
-                if (r < F.nranks) s += vals[r];
-            F.rhs[t] = s;
-            r_sh[t] = s;
-        }
-    }
-    if (F.mode == FINISH_REDUCE_SOLVE || F.mode == FINISH_EXCHANGE_SOLVE) {
+}
+
+// Small-grid solves on the reduced (and exchanged) vector r_sh[0..n) held in shared memory.
+__device__ __forceinline__ void finish_solve(const FinishParams& F, int n, double* __restrict__ sm_a)
+{
+    const int T = blockDim.x, t = threadIdx.x;
+    double* r_sh = sm_a;            // rhs (then rhs - mean)
+    double* phi_sh = sm_a + n;
+    double* g_sh = sm_a + 2 * n + 1;   // pseudo-inverse kernel G staged in shared memory by the caller
+    if (F.mode == FINISH_REDUCE_SOLVE) {
         __syncthreads();
         if (t < 32) {                // mean in a fixed order: strided lane sums, then the xor tree
             double s = 0.0;
@@ -318,10 +291,120 @@ __device__ __forceinline__ void finish_last_cta(const FinishParams& F, const dou
             F.poly[idx] = s;
         }
     }
+}
+
+// One level (n <= VM_FUSE_MAX_N, blockDim.x >= n).
+__device__ __forceinline__ void finish_last_cta(const FinishParams& F, const double* rows, int nrows, int n,
+                                                double* __restrict__ sm_a /* >= 3n + 1 doubles, free */,
+                                                double* __restrict__ scratch /* blockDim.x doubles */)
+{
+    __shared__ int s_last;
+    __threadfence();                                   // publish this CTA's row
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(F.ticket, 1u) == gridDim.x - 1u);
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const int T = blockDim.x, t = threadIdx.x;
+    double* r_sh = sm_a;
+    double* g_sh = sm_a + 2 * n + 1;   // the convolution must not chase n dependent global loads (measured: 5 us of a 17 us step floor)
+    if (F.mode == FINISH_REDUCE_SOLVE && t < n) g_sh[t] = __ldg(F.G + t);
+    int P = 1;
+    while (2 * P * n <= T && 2 * P <= nrows) P *= 2;
+    if (t < n * P) {
+        const int i = t % n, part = t / n;
+        double s = 0.0;
+        for (int r = part; r < nrows; r += 8 * P) {      // 8 independent L2 loads in flight, summed in row order
+            double vals[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int rr = r + u * P;
+                vals[u] = (rr < nrows) ? __ldcg(rows + (size_t)rr * n + i) : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) s += vals[u];
+        }
+        scratch[part * n + i] = s;
+    }
+    __syncthreads();
+    if (t < n) {
+        double s = 0.0;
+        for (int part = 0; part < P; ++part) s += scratch[part * n + t];
+        if (!F.xchg) F.rhs[t] = s;
+        r_sh[t] = s;
+    }
+    if (F.xchg) exchange_ll(F, r_sh, n, F.rhs);
+    finish_solve(F, n, sm_a);
     if (t == 0) *F.ticket = 0u;      // ready for the next launch on this stream
 }
 
+// Two levels (VM_FUSE_MAX_N < n <= VM_X_MAX_N): reduce (+ exchange) only; any CTA shape.
+__device__ __forceinline__ void finish_two_level(const FinishParams& F, const double* rows, int nrows, int n,
+                                                 double* __restrict__ sm_a /* >= n doubles, free */)
+{
+    __shared__ int s_last2;
+    const int T = blockDim.x, t = threadIdx.x;
+    const int g = blockIdx.x / VM_GROUP_CTAS, ngroups = (nrows + VM_GROUP_CTAS - 1) / VM_GROUP_CTAS;
+    const int r0 = g * VM_GROUP_CTAS, cnt = min(nrows - r0, VM_GROUP_CTAS);
+    __threadfence();                                   // publish this CTA's row
+    __syncthreads();
+    if (t == 0) s_last2 = (atomicAdd(F.ticket + 1 + g, 1u) == (unsigned)cnt - 1u);
+    __syncthreads();
+    if (!s_last2) return;
+    __threadfence();
+    for (int i = t; i < n; i += T) {                   // level 1: this group's rows, all loads in flight, row order
+        double vals[VM_GROUP_CTAS];
+#pragma unroll
+        for (int u = 0; u < VM_GROUP_CTAS; ++u) vals[u] = (u < cnt) ? __ldcg(rows + (size_t)(r0 + u) * n + i) : 0.0;
+        double s = 0.0;
+#pragma unroll
+        for (int u = 0; u < VM_GROUP_CTAS; ++u) s += vals[u];
+        F.grows[(size_t)g * n + i] = s;
+    }
+    __threadfence();
+    __syncthreads();
+    if (t == 0) {
+        F.ticket[1 + g] = 0u;
+        s_last2 = (atomicAdd(F.ticket, 1u) == (unsigned)ngroups - 1u);
+    }
+    __syncthreads();
+    if (!s_last2) return;
+    __threadfence();
+    for (int i = t; i < n; i += T) {                   // level 2: the group rows in group order
+        double s = 0.0;
+        for (int q0 = 0; q0 < ngroups; q0 += 8) {
+            double vals[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) vals[u] = (q0 + u < ngroups) ? __ldcg(F.grows + (size_t)(q0 + u) * n + i) : 0.0;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) s += vals[u];
+        }
+        if (!F.xchg) F.rhs[i] = s;
+        sm_a[i] = s;
+    }
+    if (F.xchg) exchange_ll(F, sm_a, n, F.rhs);
+    if (t == 0) *F.ticket = 0u;
+}
+
+__device__ __forceinline__ void finish_grid(const FinishParams& F, const double* rows, int nrows, int n,
+                                            double* __restrict__ sm_a, double* __restrict__ scratch)
+{
+    if (F.two_level) finish_two_level(F, rows, nrows, n, sm_a);
+    else finish_last_cta(F, rows, nrows, n, sm_a, scratch);
+}
+
 // ================================================================ host ======
+// fused peer exchange available on this context: fill the exchange fields of F and take the next sequence number
+inline bool vm_xchg_setup(vm_ctx* ctx, FinishParams& F)
+{
+    if (ctx->nranks <= 1 || !ctx->peers_connected) return false;
+    F.xchg = 1;
+    F.nranks = ctx->nranks; F.rank = ctx->rank; F.seq = ++ctx->xseq;
+    F.err = ctx->xerr;
+    for (int r = 0; r < ctx->nranks; ++r) F.peer[r] = ctx->peer_inbox[r];
+    return true;
+}
+
 struct DepositPlan {
     int var, rep_log2, grid, threads;
     size_t smem;

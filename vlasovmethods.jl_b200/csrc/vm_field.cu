@@ -94,6 +94,14 @@ __global__ void k_dcoef_from_phi(const double* __restrict__ phi, int n, double i
     if (i < n) dcoef[i] = (phi[i + 1 == n ? 0 : i + 1] - phi[i]) * inv_h;
 }
 
+// the same for every column of an n x ncols coefficient history (blockIdx.y = column)
+__global__ void k_dcoef_from_phi_cols(const double* __restrict__ phi, int n, double inv_h, double* __restrict__ dcoef)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t o = (size_t)blockIdx.y * n;
+    if (i < n) dcoef[o + i] = (phi[o + (i + 1 == n ? 0 : i + 1)] - phi[o + i]) * inv_h;
+}
+
 // ---- double-double helpers for the energy quadratic form --------------------------------------
 __device__ __forceinline__ void two_sum(double a, double b, double& s, double& e)
 {
@@ -178,7 +186,12 @@ void vm_field_reduce_rows(vm_field* f, const double* rows, int nrows, int ncols,
 void vm_field_solve_local(vm_field* f, bool allreduce)
 {
     vm_ctx* ctx = f->ctx;
-    if (allreduce) vm_allreduce_sum(ctx, f->rhs, (size_t)f->n);
+    // rhs may already hold the sum over the ranks (fused peer exchange, an earlier solve, vm_vp_run): reducing it
+    // again would scale phi by nranks -- update!(potential) of the reference can be repeated safely, so can this
+    if (allreduce && ctx->nranks > 1 && !f->rhs_global) {
+        vm_allreduce_sum(ctx, f->rhs, (size_t)f->n);
+        f->rhs_global = true;
+    }
     k_poisson_solve<<<(f->n + 31) / 32, 256, (size_t)f->n * sizeof(double), ctx->stream>>>(f->rhs, f->G, f->n, f->map.inv_h,
                                                                                           f->phi, f->dcoef);
     VM_LAUNCHED(ctx);
@@ -188,11 +201,40 @@ void vm_field_solve_local(vm_field* f, bool allreduce)
 double* vm_field_wv(vm_field* f) { return f->rhs + f->n; }
 static double* field_energy_ptr(vm_field* f) { return f->rhs + f->n + VM_DIAG_COLS; }
 
-void vm_field_energy_dev(vm_field* f)
+void vm_field_energy_dev(vm_field* f, const double* phi)
 {
     vm_ctx* ctx = f->ctx;
-    k_field_energy<<<1, 256, 0, ctx->stream>>>(f->phi, f->stencil_s, f->order, f->n, field_energy_ptr(f));
+    k_field_energy<<<1, 256, 0, ctx->stream>>>(phi ? phi : f->phi, f->stencil_s, f->order, f->n, field_energy_ptr(f));
     VM_LAUNCHED(ctx);
+}
+
+// ExternalField (src/electric_field.jl:55-77): coefficient history coeffs[:, ts], column-major n x ncols, kept on
+// the device together with the derivative-spline coefficients of every column.
+void vm_field_ext_upload(vm_field* f, const double* coeffs_host, int ncols)
+{
+    vm_ctx* ctx = f->ctx;
+    const size_t elems = (size_t)f->n * ncols;
+    if (ncols > f->ext_cols) {
+        VM_CUDA(cudaStreamSynchronize(ctx->stream));
+        cudaFree(f->ext_phi); cudaFree(f->ext_dcoef);
+        f->ext_phi = f->ext_dcoef = nullptr;
+        f->ext_cols = 0;
+        VM_CUDA(cudaMalloc(&f->ext_phi, elems * sizeof(double)));
+        VM_CUDA(cudaMalloc(&f->ext_dcoef, elems * sizeof(double)));
+        f->ext_cols = ncols;
+    }
+    VM_CUDA(cudaMemcpyAsync(f->ext_phi, coeffs_host, elems * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    k_dcoef_from_phi_cols<<<dim3((f->n + 255) / 256, ncols), 256, 0, ctx->stream>>>(f->ext_phi, f->n, f->map.inv_h, f->ext_dcoef);
+    VM_LAUNCHED(ctx);
+    VM_CUDA(cudaStreamSynchronize(ctx->stream));           // the host matrix is only borrowed for the call
+}
+
+void vm_field_ext_select(vm_field* f, int col)
+{
+    vm_ctx* ctx = f->ctx;
+    const size_t nb = (size_t)f->n * sizeof(double);
+    VM_CUDA(cudaMemcpyAsync(f->phi, f->ext_phi + (size_t)col * f->n, nb, cudaMemcpyDeviceToDevice, ctx->stream));
+    VM_CUDA(cudaMemcpyAsync(f->dcoef, f->ext_dcoef + (size_t)col * f->n, nb, cudaMemcpyDeviceToDevice, ctx->stream));
 }
 
 double* vm_field_diag_rows(vm_field* f, int rows)
@@ -288,7 +330,7 @@ int vm_field_destroy(vm_field* f)
     if (!f) return VM_OK;
     vm_child_quiesce(f->ctx, f->device);
     cudaFree(f->rhs); cudaFree(f->phi); cudaFree(f->dcoef); cudaFree(f->G);
-    cudaFree(f->stencil_s); cudaFree(f->diag);
+    cudaFree(f->stencil_s); cudaFree(f->diag); cudaFree(f->ext_phi); cudaFree(f->ext_dcoef);
     delete f;
     return VM_OK;
 }
@@ -351,7 +393,7 @@ int vm_field_energy(vm_field* f, double* W)
     VM_API_BEGIN(f ? f->ctx : nullptr)
     VM_REQUIRE(f != nullptr && W != nullptr, "vm_field_energy: NULL argument");
     vm_ctx* ctx = f->ctx;
-    vm_field_energy_dev(f);
+    vm_field_energy_dev(f, nullptr);
     double* host = vm_pinned(ctx, 1);
     VM_CUDA(cudaMemcpyAsync(host, field_energy_ptr(f), sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     VM_CUDA(cudaStreamSynchronize(ctx->stream));

@@ -18,8 +18,14 @@
 #define VM_DIAG_COLS 4          // extra columns appended to a partial row: [sum w v^2, sum w v, sum w, spare]
 #define VM_MAX_EVENTS 16
 #define VM_MAX_PEERS 8          // ranks of the fused peer-memory exchange (one NVSwitch node)
-#define VM_XSLOT 136            // doubles per (set, rank) inbox slot (>= VM_FUSE_MAX_N)
-#define VM_XFLAG_OFF (2 * VM_MAX_PEERS * VM_XSLOT)   // flags (u64) follow the slots
+#define VM_X_MAX_N 1024         // largest vector (basis functions) the fused peer exchange carries
+// Inbox of the fused exchange: [2 sets][VM_MAX_PEERS ranks][VM_XSLOT_WORDS] 64-bit words.  Every double travels as
+// two words {low 32 data bits | seq << 32}, {high 32 data bits | seq << 32} ("LL" protocol: data and flag arrive in
+// the same 8-byte store, so the sender needs no fence and the receiver no separate flag).
+#define VM_XSLOT_WORDS (2 * (VM_X_MAX_N + 8))
+#define VM_XINBOX_WORDS (2 * VM_MAX_PEERS * VM_XSLOT_WORDS)
+#define VM_MAX_GROUPS 63        // groups of CTAs in the two-level cross-CTA reduction (tickets 1 .. VM_MAX_GROUPS)
+#define VM_GROUP_CTAS 16        // CTAs per group
 
 struct vm_error : public std::runtime_error {
     int code;
@@ -57,10 +63,10 @@ struct vm_ctx {
     // communicator (one process per GPU)
     void* nccl_comm = nullptr;
     int rank = 0, nranks = 1;
-    unsigned* ticket = nullptr;          // device counter for the last-CTA finish (always zero between launches)
-    // fused peer-memory exchange (vm_ctx_peer_connect): inbox = [2 sets][VM_MAX_PEERS][VM_XSLOT] doubles + flags
-    double* inbox = nullptr;
-    double* peer_inbox[VM_MAX_PEERS] = {};
+    unsigned* ticket = nullptr;          // device counters for the last-CTA finish: [0] grid, [1 + g] group g (zero between launches)
+    // fused peer-memory exchange (vm_ctx_peer_connect): inbox = [2 sets][VM_MAX_PEERS][VM_XSLOT_WORDS] u64
+    unsigned long long* inbox = nullptr;
+    unsigned long long* peer_inbox[VM_MAX_PEERS] = {};
     bool peers_connected = false;
     unsigned long long xseq = 0;         // exchange sequence number (identical on all ranks)
     unsigned* xerr = nullptr;            // device: set when a peer wait timed out
@@ -106,6 +112,9 @@ struct vm_field {
     int order = 0, n = 0, shift = 0;
     CellMap map{};
     double *rhs = nullptr, *phi = nullptr, *dcoef = nullptr;  // device, n each
+    bool rhs_global = true;                                   // rhs holds the sum over all ranks (false: this rank's deposit only)
+    double *ext_phi = nullptr, *ext_dcoef = nullptr;          // device: coefficient history of vm_vp_run_external (n x ext_cols)
+    int ext_cols = 0;
     double *G = nullptr;                                      // device: circulant pseudo-inverse kernel (first column)
     double *stencil_s = nullptr;                              // device: stiffness stencil, 2k-1 entries
     double *diag = nullptr;                                   // device: [W, K, M, sum_w] rows

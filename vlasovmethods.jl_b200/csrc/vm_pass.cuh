@@ -233,7 +233,7 @@ k_vp_pass(double* __restrict__ x, double* __restrict__ v, const double* __restri
         }
     }
     flush_grid<VAR>(grid, scratch, out, n, GHOST, P.rep_log2, nwarps, P.ncols);
-    if (VAR != VAR_ATOMIC && F.mode != FINISH_NONE) finish_last_cta(F, out, gridDim.x, n, grid, scratch);
+    if (VAR != VAR_ATOMIC && F.mode != FINISH_NONE) finish_grid(F, out, gridDim.x, n, grid, scratch);
 }
 
 // ================================================================ host ======

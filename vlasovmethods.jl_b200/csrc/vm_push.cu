@@ -164,6 +164,28 @@ __global__ void __launch_bounds__(512, 2) k_drift(double* __restrict__ x, const 
         st_stream(x + p, __dadd_rn(ld_stream(x + p), __dmul_rn(dt, ld_stream(v + p))));
 }
 
+// One stage of the classical RK4 scheme for zdot = lorentz_force(z) with low storage: accumulators (ax, av) and
+// the next stage state (xs, vs); kx = stage velocity, kv = a (the gathered -phi').
+__global__ void __launch_bounds__(512, 2)
+k_rk4_stage(double* __restrict__ x, double* __restrict__ v, const double* __restrict__ a, double* __restrict__ xs,
+            double* __restrict__ vs, double* __restrict__ ax, double* __restrict__ av, long n, double cdt_next,
+            double bdt, int stage)
+{
+    const long stride = (long)gridDim.x * blockDim.x;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const double kx = stage == 0 ? v[i] : vs[i], kv = a[i];
+        const double sx = (stage == 0 ? 0.0 : ax[i]) + bdt * kx, sv = (stage == 0 ? 0.0 : av[i]) + bdt * kv;
+        if (stage < 3) {
+            ax[i] = sx; av[i] = sv;
+            xs[i] = x[i] + cdt_next * kx;
+            vs[i] = v[i] + cdt_next * kv;
+        } else {
+            x[i] += sx;
+            v[i] += sv;
+        }
+    }
+}
+
 // ================================================================ host ======
 // one translation unit per spline order (vm_pass_order.cu)
 #define VM_DECL_PASS(k)                                                                                                   \
@@ -188,23 +210,25 @@ void launch_pass(vm_ctx* ctx, int mode, int order, const DepositPlan& pl, double
 }
 
 template <int K>
-void launch_push_inst(vm_ctx* ctx, vm_field* f, vm_particles* p, double* out, const PassParams& P)
+void launch_push_inst(vm_ctx* ctx, vm_field* f, vm_particles* p, double* out, const PassParams& P, const double* dcoef)
 {
     int grid, threads;
     vm_launch_geometry(ctx, &grid, &threads);
     if (threads > 512) threads = 512;
-    k_vp_push<K><<<grid, threads, (size_t)(f->n + K) * sizeof(double), ctx->stream>>>(p->x, p->v, p->w, f->dcoef, out, P);
+    k_vp_push<K><<<grid, threads, (size_t)(f->n + K) * sizeof(double), ctx->stream>>>(p->x, p->v, p->w, dcoef, out, P);
     VM_LAUNCHED(ctx);
 }
 
-void launch_push(vm_ctx* ctx, vm_field* f, vm_particles* p, double* out, const PassParams& P)
+// dcoef: derivative-spline coefficients to gather from (default: the field's current ones)
+void launch_push(vm_ctx* ctx, vm_field* f, vm_particles* p, double* out, const PassParams& P, const double* dcoef = nullptr)
 {
+    if (!dcoef) dcoef = f->dcoef;
     switch (f->order) {
-        case 2: launch_push_inst<2>(ctx, f, p, out, P); break;
-        case 3: launch_push_inst<3>(ctx, f, p, out, P); break;
-        case 4: launch_push_inst<4>(ctx, f, p, out, P); break;
-        case 5: launch_push_inst<5>(ctx, f, p, out, P); break;
-        case 6: launch_push_inst<6>(ctx, f, p, out, P); break;
+        case 2: launch_push_inst<2>(ctx, f, p, out, P, dcoef); break;
+        case 3: launch_push_inst<3>(ctx, f, p, out, P, dcoef); break;
+        case 4: launch_push_inst<4>(ctx, f, p, out, P, dcoef); break;
+        case 5: launch_push_inst<5>(ctx, f, p, out, P, dcoef); break;
+        case 6: launch_push_inst<6>(ctx, f, p, out, P, dcoef); break;
         default: throw vm_error(VM_ERR_UNSUPPORTED, "spline order must be in 2..6");
     }
 }
@@ -227,7 +251,9 @@ void launch_gather_inst(vm_ctx* ctx, vm_field* f, const double* x, long np, doub
 // internal entry points shared with vm_field.cu ------------------------------------------------
 void vm_field_reduce_rows(vm_field* f, const double* rows, int nrows, int ncols, double* out);   // vm_field.cu
 void vm_field_solve_local(vm_field* f, bool allreduce);                                            // vm_field.cu
-void vm_field_energy_dev(vm_field* f);                                                             // vm_field.cu
+void vm_field_energy_dev(vm_field* f, const double* phi = nullptr);                                // vm_field.cu
+void vm_field_ext_upload(vm_field* f, const double* coeffs_host, int ncols);                       // vm_field.cu
+void vm_field_ext_select(vm_field* f, int col);                                                    // vm_field.cu
 void vm_field_store_diag(vm_field* f, int row, double chi);                                        // vm_field.cu
 double* vm_field_wv(vm_field* f);                                                                  // vm_field.cu
 double* vm_field_diag_rows(vm_field* f, int rows);                                                 // vm_field.cu
@@ -249,7 +275,7 @@ void vm_gather_dev(vm_field* f, const double* x_dev, long np, double* e_dev, dou
 // want_solve: also produce phi/dcoef (all-reduce + replicated solve); on a single GPU with a small
 // grid both the reduction and the solve are fused into the pass kernel's last CTA.
 static void pass_with_deposit(vm_field* f, vm_particles* p, int pass_mode, int deposit_mode, PassParams P,
-                              bool want_solve, bool prof_deposit = false)
+                              bool want_solve, bool prof_deposit = false, double* xsrc = nullptr /* deposit-only: positions to use */)
 {
     vm_ctx* ctx = f->ctx;
     const int n = f->n;
@@ -269,28 +295,31 @@ static void pass_with_deposit(vm_field* f, vm_particles* p, int pass_mode, int d
         VM_CUDA(cudaMemsetAsync(f->rhs, 0, (size_t)ncols * sizeof(double), ctx->stream));
         out = f->rhs;
     } else {
-        out = vm_partials(ctx, (size_t)pl.grid * ncols);
-        const size_t gdoubles = ((size_t)(n + f->order - 1) << pl.rep_log2) * (size_t)(pl.var == VAR_ATOMIC ? 1 : pl.threads / 32);
-        // the last-CTA finish works with one thread per basis function (hand-tuned CTA shapes may be smaller)
+        const int ngroups = (pl.grid + VM_GROUP_CTAS - 1) / VM_GROUP_CTAS;
+        out = vm_partials(ctx, (size_t)(pl.grid + ngroups) * ncols);
+        const size_t gdoubles = ((size_t)(n + f->order - 1) << pl.rep_log2) * (size_t)(pl.threads / 32);
+        const bool xchg = want_solve && ctx->nranks > 1 && ctx->peers_connected && n <= VM_X_MAX_N;
+        F.ticket = ctx->ticket;
+        F.rhs = f->rhs; F.G = f->G; F.phi = f->phi; F.dcoef = f->dcoef; F.inv_h = f->map.inv_h;
+        // the one-level finish works with one thread per basis function (hand-tuned CTA shapes may be smaller)
         if (n <= VM_FUSE_MAX_N && !ctx->no_fuse && gdoubles >= (size_t)3 * n + 1 && pl.threads >= n) {
-            F.mode = (want_solve && ctx->nranks == 1) ? FINISH_REDUCE_SOLVE : FINISH_REDUCE;
-            F.ticket = ctx->ticket;
-            F.rhs = f->rhs; F.G = f->G; F.phi = f->phi; F.dcoef = f->dcoef; F.inv_h = f->map.inv_h;
-            if (want_solve && ctx->nranks > 1 && ctx->peers_connected && n <= VM_XSLOT) {
-                F.mode = FINISH_EXCHANGE_SOLVE;       // deposit + all-gather over NVLink + solve in one kernel
-                F.nranks = ctx->nranks; F.rank = ctx->rank; F.seq = ++ctx->xseq;
-                F.inbox = ctx->inbox; F.err = ctx->xerr;
-                for (int r = 0; r < ctx->nranks; ++r) F.peer[r] = ctx->peer_inbox[r];
-            }
+            // single GPU, or all ranks connected through peer memory: reduce + (exchange) + solve in the pass kernel
+            F.mode = (want_solve && (ctx->nranks == 1 || xchg)) ? FINISH_REDUCE_SOLVE : FINISH_REDUCE;
+        } else if (n <= VM_X_MAX_N && !ctx->no_fuse && gdoubles >= (size_t)n && ngroups <= VM_MAX_GROUPS) {
+            F.mode = FINISH_REDUCE;               // two-level reduce (+ exchange); the solve is its own multi-CTA kernel
+            F.two_level = 1;
+            F.grows = out + (size_t)pl.grid * ncols;
         }
+        if (F.mode != FINISH_NONE && xchg) vm_xchg_setup(ctx, F);   // deposit + all-gather over NVLink (+ solve) in one kernel
     }
     // the dominant kernel of its caller: the fused pass inside vm_vp_run, the deposit pass elsewhere
     const bool prof = (pass_mode == MODE_PUSH_DEPOSIT) || (pass_mode == MODE_DEPOSIT && prof_deposit);
     if (prof) vm_prof_mark(ctx);
-    launch_pass(ctx, pass_mode, f->order, pl, p->x, p->v, p->w, f->dcoef, out, P, F);
+    launch_pass(ctx, pass_mode, f->order, pl, xsrc ? xsrc : p->x, p->v, p->w, f->dcoef, out, P, F);
     if (prof) vm_prof_mark(ctx);
     if (pl.var != VAR_ATOMIC && F.mode == FINISH_NONE) vm_field_reduce_rows(f, out, pl.grid, ncols, f->rhs);
-    if (want_solve && F.mode != FINISH_REDUCE_SOLVE && F.mode != FINISH_EXCHANGE_SOLVE) vm_field_solve_local(f, true);
+    f->rhs_global = (ctx->nranks == 1) || F.xchg;
+    if (want_solve && F.mode != FINISH_REDUCE_SOLVE) vm_field_solve_local(f, true);
 }
 
 static void wv_moments(vm_field* f, vm_particles* p)
@@ -468,8 +497,8 @@ int vm_vp_run(vm_field* f, vm_particles* p, double dt, int nsteps, int diag_ever
         vm_field_store_diag(f, row++, chi);
     };
 
-    if (p->n == 0) nsteps = 0;
-    if (diag_every > 0 && p->n > 0) record_diag(false);
+    // a rank with an empty shard still runs every pass: it takes part in the exchanges / all-reduces of the others
+    if (diag_every > 0) record_diag(false);
     bool staggered = false;   // true: x holds x^n + dt/2 v^n and f holds phi of those positions
     for (int s = 1; s <= nsteps; ++s) {
         const bool is_diag = diag_every > 0 && (s % diag_every == 0);
@@ -525,6 +554,109 @@ int vm_vp_run(vm_field* f, vm_particles* p, double dt, int nsteps, int diag_ever
             VM_CUDA(cudaMemcpyAsync(host, rows, (size_t)row * 4 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
             VM_CUDA(cudaStreamSynchronize(ctx->stream));
             for (int i = 0; i < row * 4; ++i) diag_host[i] = host[i];
+        }
+    }
+    VM_API_END
+}
+
+int vm_vp_run_external(vm_field* f, vm_particles* p, double dt, int nsteps, int diag_every, double chi,
+                       const double* coeffs_host, int ncols, double coeff_dt, double* diag_host)
+{
+    VM_API_BEGIN(f ? f->ctx : nullptr)
+    check_pair(f, p, "vm_vp_run_external");
+    VM_REQUIRE(nsteps >= 0 && diag_every >= 0 && chi != 0.0, "vm_vp_run_external: bad argument");
+    VM_REQUIRE(coeffs_host != nullptr && ncols >= 1 && coeff_dt > 0.0, "vm_vp_run_external: bad coefficient history");
+    VM_REQUIRE(diag_every == 0 || diag_host != nullptr, "vm_vp_run_external: diag_host is NULL");
+    vm_ctx* ctx = f->ctx;
+    // update!(::ExternalField, x, w, t): ts = round(t / dt_coeffs), phi = coeffs[:, ts]  (src/electric_field.jl:66-69;
+    // Julia's round: ties to even, as nearbyint in the default rounding mode)
+    auto col_of = [&](int it) {
+        const double ts = nearbyint((it * dt) / coeff_dt);
+        VM_REQUIRE(ts >= 0.0 && ts < (double)ncols, "vm_vp_run_external: time index outside the coefficient history");
+        return (int)ts;
+    };
+    for (int it = 0; it <= nsteps; ++it) (void)col_of(it);          // validate before touching the state
+    vm_field_ext_upload(f, coeffs_host, ncols);
+    const double dte = dt * chi;                           // effective step (src/vlasov_poisson.jl:80)
+    const double kick_full = dte * (-1.0 / (chi * chi));   // v += dte * E / chi^2, E = -phi'
+    const double hd = 0.5 * dte;
+    const int nrows = diag_every > 0 ? nsteps / diag_every + 1 : 0;
+    double* rows = nrows ? vm_field_diag_rows(f, nrows) : nullptr;
+    int grid, threads;
+    vm_launch_geometry(ctx, &grid, &threads);
+    if (threads > 512) threads = 512;
+    int row = 0;
+    if (diag_every > 0) {                                  // update!(efield, x, w, 0.0); save_timestep!(IC, efield, 1)
+        vm_field_energy_dev(f, f->ext_phi + (size_t)col_of(0) * f->n);
+        wv_moments(f, p);
+        vm_field_store_diag(f, row++, chi);
+    }
+    int last_col = col_of(0);
+    for (int it = 1; it <= nsteps; ++it) {
+        const bool is_diag = diag_every > 0 && (it % diag_every == 0);
+        const int col = col_of(it);
+        last_col = col;
+        PassParams P{};
+        P.map = f->map; P.n = p->n;
+        P.drift0 = hd; P.kick = kick_full; P.drift1 = hd; P.diag = is_diag;
+        double* out = is_diag ? vm_partials(ctx, (size_t)grid * VM_DIAG_COLS) : nullptr;
+        launch_push(ctx, f, p, out, P, f->ext_dcoef + (size_t)col * f->n);
+        if (is_diag) {
+            vm_field_reduce_rows(f, out, grid, VM_DIAG_COLS, vm_field_wv(f));
+            vm_allreduce_sum(ctx, vm_field_wv(f), VM_DIAG_COLS);
+            vm_field_energy_dev(f, f->ext_phi + (size_t)col * f->n);
+            vm_field_store_diag(f, row++, chi);
+        }
+    }
+    vm_field_ext_select(f, last_col);                      // poisson.phi of the reference holds the last prescribed column
+    if (nrows > 0) {
+        double* host = vm_pinned(ctx, (size_t)nrows * 4);
+        VM_CUDA(cudaMemcpyAsync(host, rows, (size_t)row * 4 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        VM_CUDA(cudaStreamSynchronize(ctx->stream));
+        for (int i = 0; i < nrows * 4; ++i) diag_host[i] = i < row * 4 ? host[i] : 0.0;
+    }
+    VM_API_END
+}
+
+int vm_vp_vector_field(vm_field* f, vm_particles* p, int flags, double* xdot_host, double* vdot_host)
+{
+    VM_API_BEGIN(f ? f->ctx : nullptr)
+    check_pair(f, p, "vm_vp_vector_field");
+    vm_ctx* ctx = f->ctx;
+    if (!(flags & VM_VF_KEEP_POTENTIAL)) {                 // update_potential!(model): projection! + update!
+        PassParams D{};
+        pass_with_deposit(f, p, MODE_DEPOSIT, VM_DEPOSIT_DETERMINISTIC, D, true);
+    }
+    if (!p->a) VM_CUDA(cudaMalloc(&p->a, (size_t)(p->n > 0 ? p->n : 1) * sizeof(double)));
+    if (p->n > 0) vm_gather_dev(f, p->x, p->n, p->a, -1.0, 1);      // vdot = -phi'(x); xdot is the v array itself
+    if (xdot_host && p->n > 0) VM_CUDA(cudaMemcpyAsync(xdot_host, p->v, (size_t)p->n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (vdot_host && p->n > 0) VM_CUDA(cudaMemcpyAsync(vdot_host, p->a, (size_t)p->n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (xdot_host || vdot_host) VM_CUDA(cudaStreamSynchronize(ctx->stream));
+    VM_API_END
+}
+
+int vm_vp_rk4_run(vm_field* f, vm_particles* p, double dt, int nsteps)
+{
+    VM_API_BEGIN(f ? f->ctx : nullptr)
+    check_pair(f, p, "vm_vp_rk4_run");
+    VM_REQUIRE(nsteps >= 0, "vm_vp_rk4_run: bad argument");
+    vm_ctx* ctx = f->ctx;
+    const size_t bytes = (size_t)(p->n > 0 ? p->n : 1) * sizeof(double);
+    for (int i = 0; i < 4; ++i) if (!p->work[i]) VM_CUDA(cudaMalloc(&p->work[i], bytes));
+    if (!p->a) VM_CUDA(cudaMalloc(&p->a, bytes));
+    double *xs = p->work[0], *vs = p->work[1], *ax = p->work[2], *av = p->work[3];
+    int grid, threads;
+    vm_launch_geometry(ctx, &grid, &threads);
+    if (threads > 512) threads = 512;
+    const double c_next[4] = {0.5, 0.5, 1.0, 0.0}, bw[4] = {1.0 / 6.0, 2.0 / 6.0, 2.0 / 6.0, 1.0 / 6.0};
+    for (int s = 0; s < nsteps; ++s) {
+        for (int st = 0; st < 4; ++st) {
+            double* xq = st == 0 ? p->x : xs;                      // lorentz_force! at the stage state:
+            PassParams D{};
+            pass_with_deposit(f, p, MODE_DEPOSIT, VM_DEPOSIT_DETERMINISTIC, D, true, false, xq);   // update_potential!
+            if (p->n > 0) vm_gather_dev(f, xq, p->n, p->a, -1.0, 1);                                // vdot = -phi'(x)
+            k_rk4_stage<<<grid, threads, 0, ctx->stream>>>(p->x, p->v, p->a, xs, vs, ax, av, p->n, c_next[st] * dt, bw[st] * dt, st);
+            VM_LAUNCHED(ctx);
         }
     }
     VM_API_END

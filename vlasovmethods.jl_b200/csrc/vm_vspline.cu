@@ -141,7 +141,7 @@ k_v_deposit(const double* __restrict__ v, const double* __restrict__ w, long np,
                              rep_log2, rep, lane);
     }
     flush_grid<VAR>(grid, scratch, out, npar, 0, rep_log2, nwarps, npar);
-    if (VAR != VAR_ATOMIC && F.mode != FINISH_NONE) finish_last_cta(F, out, gridDim.x, npar, grid, scratch);
+    if (VAR != VAR_ATOMIC && F.mode != FINISH_NONE) finish_grid(F, out, gridDim.x, npar, grid, scratch);
 }
 
 // ------------------------------------------------------------- small solves -
@@ -338,7 +338,7 @@ k_lb_stage(const double* v, const double* __restrict__ w, long np, VCell m, cons
         }
     }
     flush_grid<VAR>(grid, scratch, out, npar, 0, rep_log2, nwarps, npar);
-    if (F.mode != FINISH_NONE) finish_last_cta(F, out, gridDim.x, npar, grid, scratch);
+    if (F.mode != FINISH_NONE) finish_grid(F, out, gridDim.x, npar, grid, scratch);
 }
 
 // Streaming helper: each thread handles U pairs (4 particles for U = 2) per iteration, all loads issued
@@ -361,7 +361,7 @@ __device__ __forceinline__ void clb_coefficients(double* __restrict__ mom)
 template <int K>
 __global__ void __launch_bounds__(512, 2)
 k_v_moments(const double* __restrict__ v, long np, VCell m, const double* __restrict__ poly, double* __restrict__ out,
-            unsigned* ticket, double* __restrict__ mom)
+            unsigned* ticket, double* __restrict__ mom, const FinishParams X /* xchg fields only */)
 {
     extern __shared__ double psh[];
     load_poly<K>(psh, poly, m.ncell);
@@ -422,11 +422,14 @@ k_v_moments(const double* __restrict__ v, long np, VCell m, const double* __rest
             fin[ch][c] = t;
         }
         __syncthreads();
+        __shared__ double xv[8];
         if (threadIdx.x < 8) {
             double t = 0.0;
             for (int q = 0; q < 32; ++q) t += fin[q][threadIdx.x];
-            if (threadIdx.x < 5) mom[threadIdx.x] = t;
+            if (threadIdx.x < 5 && !X.xchg) mom[threadIdx.x] = t;
+            xv[threadIdx.x] = threadIdx.x < 5 ? t : 0.0;
         }
+        if (X.xchg) exchange_ll(X, xv, 8, mom);      // the five sums of all ranks, rank order (mom[5..7] are rewritten below)
         __syncthreads();
         if (threadIdx.x == 0) {
             __threadfence();
@@ -591,6 +594,14 @@ VCell vcell(const vm_vspline* s)
     return m;
 }
 
+// the per-cell polynomial table of a large basis exceeds the 48 KB a kernel gets without opting in
+template <typename Kern>
+void vsmem_optin(Kern kern, vm_ctx* ctx, size_t smem)
+{
+    if (smem > 48 * 1024) VM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    (void)ctx;
+}
+
 void geometry(vm_ctx* ctx, int* grid, int* threads)
 {
     vm_launch_geometry(ctx, grid, threads);
@@ -654,8 +665,8 @@ VDepSetup vdep_setup(vm_vspline* s, int extra_doubles)
         d.F.mode = FINISH_REDUCE;           // last CTA sums the per-CTA rows in a fixed order
         d.F.ticket = ctx->ticket;
         d.F.rhs = s->rhs;
-        if (ctx->nranks == 1) {             // single GPU: the mass solve and the polynomial table too
-            d.F.mode = FINISH_REDUCE_VSOLVE;
+        if (ctx->nranks == 1 || vm_xchg_setup(ctx, d.F)) {   // single GPU, or ranks connected through peer memory:
+            d.F.mode = FINISH_REDUCE_VSOLVE;                 // (exchange,) mass solve and polynomial table too
             d.F.minv = s->minv; d.F.cellpoly = s->cellpoly; d.F.coef = s->coef; d.F.poly = s->poly;
             d.F.nv = s->nv; d.F.off = s->bc ? 1 : 0; d.F.ncell = s->ncell; d.F.k = s->order;
         }
@@ -736,9 +747,12 @@ void moments_dev(vm_vspline* s, const double* v, long np, int conservative)
         if (threads < 256) threads = 256;             // the fused finish uses 256 threads
         double* out = vm_partials(ctx, (size_t)grid * 8);
         const size_t smem = (size_t)s->ncell * (s->order | 1) * sizeof(double);
-        const bool fuse = ctx->nranks == 1 && !ctx->no_fuse;
+        const bool fuse = (ctx->nranks == 1 || ctx->peers_connected) && !ctx->no_fuse;
         unsigned* ticket = fuse ? ctx->ticket : nullptr;
-        VM_ORDER_SWITCH(s->order, k_v_moments<K><<<grid, threads, smem, ctx->stream>>>(v, np, vcell(s), s->poly, out, ticket, s->moments));
+        FinishParams X{};
+        if (fuse) vm_xchg_setup(ctx, X);
+        VM_ORDER_SWITCH(s->order, vsmem_optin(k_v_moments<K>, ctx, smem);
+                        k_v_moments<K><<<grid, threads, smem, ctx->stream>>>(v, np, vcell(s), s->poly, out, ticket, s->moments, X));
         VM_LAUNCHED(ctx);
         if (fuse) return;                             // sums + A1, A2 done by the last CTA
         k_reduce_rows8<<<1, 256, 0, ctx->stream>>>(out, grid, s->moments);
@@ -761,7 +775,8 @@ void rhs_dev(vm_vspline* s, const double* v, const double* w, long np, double nu
     int grid, threads;
     geometry(ctx, &grid, &threads);
     const size_t smem = (size_t)s->ncell * (s->order | 1) * sizeof(double);
-    VM_ORDER_SWITCH(s->order, k_v_rhs<K><<<grid, threads, smem, ctx->stream>>>(v, np, vcell(s), s->poly, s->moments, nu, vdot));
+    VM_ORDER_SWITCH(s->order, vsmem_optin(k_v_rhs<K>, ctx, smem);
+                    k_v_rhs<K><<<grid, threads, smem, ctx->stream>>>(v, np, vcell(s), s->poly, s->moments, nu, vdot));
     VM_LAUNCHED(ctx);
 }
 
@@ -844,7 +859,9 @@ int vm_vspline_create(vm_ctx* ctx, double vmin, double vmax, int nknots, int ord
         VM_CUDA(cudaMemcpyAsync(s->minv, minv.data(), minv.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
         VM_CUDA(cudaMemcpyAsync(s->cellpoly, cp.data(), cp.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
         VM_CUDA(cudaStreamSynchronize(ctx->stream));
-        VM_REQUIRE((size_t)s->ncell * k * sizeof(double) <= 160 * 1024, "vm_vspline_create: polynomial table exceeds shared memory");
+        // the evaluation kernels keep the per-cell polynomial table (row stride order | 1) in shared memory, two CTAs per SM
+        VM_REQUIRE((size_t)s->ncell * (k | 1) * sizeof(double) <= (ctx->smem_optin < 100 * 1024 ? ctx->smem_optin : 100 * 1024),
+                   "vm_vspline_create: polynomial table exceeds shared memory (too many knots for this order)");
     } catch (...) {
         vm_vspline_destroy(s);
         throw;
@@ -913,6 +930,54 @@ int vm_vproject(vm_vspline* s, vm_particles* p)
     VM_API_END
 }
 
+// replacement velocities (stage values of a user-side integrator) go into a scratch array: the particle state
+// itself is not touched, as in the reference, where `projection(v, dist, sdist)` only reads dist.particles.w
+static double* upload_scratch_v(vm_particles* p, const double* v_host)
+{
+    double* q = work_array(p, 4);
+    if (p->n > 0)
+        VM_CUDA(cudaMemcpyAsync(q, v_host, (size_t)p->n * sizeof(double), cudaMemcpyHostToDevice, p->ctx->stream));
+    return q;
+}
+
+int vm_vproject_at(vm_vspline* s, vm_particles* p, const double* v_host)
+{
+    VM_API_BEGIN(s ? s->ctx : nullptr)
+    check_pair(s, p, "vm_vproject_at");
+    VM_REQUIRE(v_host != nullptr || p->n == 0, "vm_vproject_at: v_host is NULL");
+    project_dev(s, upload_scratch_v(p, v_host), p->w, p->n);
+    VM_CUDA(cudaStreamSynchronize(s->ctx->stream));      // the host array is only borrowed for the call
+    VM_API_END
+}
+
+int vm_lb_rhs_at(vm_vspline* s, vm_particles* p, const double* v_host, double nu, int conservative, double* vdot_host)
+{
+    VM_API_BEGIN(s ? s->ctx : nullptr)
+    check_pair(s, p, "vm_lb_rhs_at");
+    VM_REQUIRE(v_host != nullptr || p->n == 0, "vm_lb_rhs_at: v_host is NULL");
+    vm_ctx* ctx = s->ctx;
+    if (!p->a) VM_CUDA(cudaMalloc(&p->a, (size_t)(p->n > 0 ? p->n : 1) * sizeof(double)));
+    rhs_dev(s, upload_scratch_v(p, v_host), p->w, p->n, nu, conservative, p->a);
+    if (vdot_host && p->n > 0) VM_CUDA(cudaMemcpyAsync(vdot_host, p->a, (size_t)p->n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    VM_CUDA(cudaStreamSynchronize(ctx->stream));
+    VM_API_END
+}
+
+int vm_vmoments_at(vm_vspline* s, vm_particles* p, const double* v_host, double* out5, double* A2)
+{
+    VM_API_BEGIN(s ? s->ctx : nullptr)
+    check_pair(s, p, "vm_vmoments_at");
+    VM_REQUIRE(v_host != nullptr || p->n == 0, "vm_vmoments_at: v_host is NULL");
+    vm_ctx* ctx = s->ctx;
+    moments_dev(s, upload_scratch_v(p, v_host), p->n, 1);
+    double* host = vm_pinned(ctx, 8);
+    VM_CUDA(cudaMemcpyAsync(host, s->moments, 8 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    VM_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (out5) for (int i = 0; i < 5; ++i) out5[i] = host[i];
+    if (A2) { A2[0] = host[5]; A2[1] = host[6]; }
+    VM_API_END
+}
+
 int vm_vspline_eval(vm_vspline* s, const double* v_host, long n, double* f_host, double* df_host)
 {
     VM_API_BEGIN(s ? s->ctx : nullptr)
@@ -926,7 +991,8 @@ int vm_vspline_eval(vm_vspline* s, const double* v_host, long n, double* f_host,
             int grid = (int)((n + 255) / 256);
             if (grid > ctx->sm_count * 4) grid = ctx->sm_count * 4;
             const size_t smem = (size_t)s->ncell * (s->order | 1) * sizeof(double);
-            VM_ORDER_SWITCH(s->order, k_v_eval<K><<<grid, 256, smem, ctx->stream>>>(buf, n, vcell(s), s->poly, buf + n, buf + 2 * n));
+            VM_ORDER_SWITCH(s->order, vsmem_optin(k_v_eval<K>, ctx, smem);
+                            k_v_eval<K><<<grid, 256, smem, ctx->stream>>>(buf, n, vcell(s), s->poly, buf + n, buf + 2 * n));
             VM_LAUNCHED(ctx);
             if (f_host) VM_CUDA(cudaMemcpyAsync(f_host, buf + n, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
             if (df_host) VM_CUDA(cudaMemcpyAsync(df_host, buf + 2 * n, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
@@ -997,7 +1063,7 @@ int vm_lb_rk438_run(vm_vspline* s, vm_particles* p, double dt, int nsteps, doubl
         ++row;
     };
     if (nrows > 0) record(0.0);
-    if (np > 0 && nsteps > 0) {
+    if (nsteps > 0) {      // (an empty shard still runs every pass: it takes part in the other ranks' exchanges)
         double *k1 = work_array(p, 0), *k2 = work_array(p, 1), *k3 = work_array(p, 2), *q = work_array(p, 4);
         // classical 3/8 rule (GeometricIntegrators RK438): a21=1/3; a31=-1/3, a32=1; a41=1, a42=-1, a43=1
         const double a21 = 1.0 / 3.0, a31 = -1.0 / 3.0;

@@ -143,6 +143,13 @@ class VPIntegratorCache:                  # :21-56
         self.A = np.zeros((n, ns)) if trajectories else None
 
 
+def _run_external_from(fld, dev, dt, steps, inner, steps_done, diag_every, χ):
+    """Continue an ExternalField run after `steps_done` steps: vm_vp_run_external counts time from 0, so the
+    coefficient history is handed over re-indexed (column j of the slice = round((steps_done + it) dt / Δt))."""
+    cols = [int(round((steps_done + it) * dt / inner.Δt)) for it in range(steps + 1)]      # update!: ts = round(t / Δt)
+    return fld.run_external(dev, dt, steps, inner.coeffs[:, cols], dt, diag_every, χ)
+
+
 def integrate_vp_(P, efield: ElectricField, parameters, IP: VPIntegratorParameters,
                   IC: Optional[VPIntegratorCache] = None, *, save: bool = True):
     """integrate_vp!(P, efield, parameters, IP, IC) (src/vlasov_poisson.jl:70-119).
@@ -151,8 +158,7 @@ def integrate_vp_(P, efield: ElectricField, parameters, IP: VPIntegratorParamete
     IC = IC or VPIntegratorCache(IP)
     χ = float(parameters["χ"] if isinstance(parameters, dict) else getattr(parameters, "χ"))
     inner = efield.field if isinstance(efield, ScaledField) else efield
-    if isinstance(inner, ExternalField):
-        raise NotImplementedError("integrate_vp_ drives self-consistent PoissonField runs")
+    external = isinstance(inner, ExternalField)
     poisson = _poisson_of(efield)
     fld = poisson.field
     n = IP.nₚ
@@ -161,24 +167,39 @@ def integrate_vp_(P, efield: ElectricField, parameters, IP: VPIntegratorParamete
     IC.w[:] = np.asarray(P.w).reshape(-1)
     nsave = IP.nₜ // (IP.nₛ - 1) if IP.nₛ > 1 else 0               # :77
     need_hist = save and (IC.X is not None)
+    t_done = [0]                                                   # steps taken so far (ExternalField indexes by time)
+
+    def advance(steps, diag_every):
+        if external:      # prescribed phi(t): no deposit / solve, the coefficient history stays on the device
+            d = _run_external_from(fld, dev, IP.dt, steps, inner, t_done[0], diag_every, χ)
+            inner.ts = int(round((t_done[0] + steps) * IP.dt / inner.Δt))
+        else:
+            d = fld.run(dev, IP.dt, steps, diag_every, 0, χ)
+        t_done[0] += steps
+        return d
+
     if not need_hist:
-        diag = fld.run(dev, IP.dt, IP.nₜ, nsave if save else 0, 0, χ)
+        diag = advance(IP.nₜ, nsave if save else 0)
         if save and diag is not None:
             m = min(diag.shape[0], IP.nₛ)
             IC.W[:m], IC.K[:m], IC.M[:m] = diag[:m, 0], diag[:m, 1], diag[:m, 2]
     else:
         def snapshot(ts):
-            d = fld.diagnostics(dev, χ)
+            x, v, _ = dev.download(w=False)
+            if external:      # update!(efield, x, w, t) only selects the column; K, M on the host (trajectory mode is small-N)
+                update_(inner, None, None, t_done[0] * IP.dt)
+                d = [energy(efield), 0.5 * float(np.dot(IC.w * v, v)), float(np.dot(IC.w, v))]
+            else:
+                d = fld.diagnostics(dev, χ)
             IC.W[ts], IC.K[ts], IC.M[ts] = d[0], d[1], d[2]
             IC.Φ[:, ts] = fld.coefficients
-            x, v, _ = dev.download(w=False)
             IC.X[:, ts], IC.V[:, ts] = x, v
             IC.A[:, ts] = fld.gather_E(dev, 1.0 / χ ** 2)
         snapshot(0)
         done, ts = 0, 0
         while done < IP.nₜ:
             step = min(nsave, IP.nₜ - done) if nsave > 0 else IP.nₜ - done
-            fld.run(dev, IP.dt, step, 0, 0, χ)
+            advance(step, 0)
             done += step
             if nsave > 0 and done % nsave == 0 and ts + 1 < IP.nₛ:
                 ts += 1
