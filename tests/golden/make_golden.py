@@ -63,6 +63,22 @@ def build():
     return out
 
 
+INPUT_KEYS = ("vp_x", "vp_v", "vp_w", "st_x", "st_v", "lb_v", "lb_w")
+
+
+def write_inputs(out):
+    """The seeded INPUT arrays as raw little-endian Float64 files (tests/golden/inputs_v1/<key>.f64): what
+    julia/make_reference_fixtures.jl reads to run the unmodified reference on the very same particles (Julia's
+    standard library reads them with read!; no .npz reader is needed on that side)."""
+    d = Path(__file__).with_name("inputs_v1")
+    d.mkdir(exist_ok=True)
+    for key in INPUT_KEYS:
+        np.ascontiguousarray(out[key], dtype="<f8").tofile(d / f"{key}.f64")
+    return d
+
+
 if __name__ == "__main__":
-    np.savez_compressed(Path(__file__).with_name("golden_v1.npz"), **build())
+    out = build()
+    np.savez_compressed(Path(__file__).with_name("golden_v1.npz"), **out)
     print("wrote", Path(__file__).with_name("golden_v1.npz"))
+    print("wrote", write_inputs(out))

@@ -396,20 +396,23 @@ def test_vspline_projection_and_rhs(vm, oracle, ctx, rng, nknots, k):
     vs.project(p)
     coef, rhs = oracle.vproject(v, w, a, b, nknots, k, M)
     assert relmax(vs.rhs, rhs) <= RTOL
-    assert relmax(vs.coefficients, coef) <= 1e-11
+    # round 2: asserted at the north star's 1e-12 (measured 1e-16 .. 2e-14, tests/test_gpu_round2.py prints them);
+    # the 300-knot order-6 basis has a mass matrix of condition ~1e3 and gets 1e-11
+    tol = 1e-11 if nknots >= 300 else 1e-12
+    assert relmax(vs.coefficients, coef) <= tol
     pts = np.concatenate([rng.uniform(a, b, 500), [a, b, a - 1, b + 1]])
     f, df = vs.eval(pts)
     fr, dfr = oracle.vspline_eval(pts, a, b, nknots, k, coef)
-    assert relmax(f, fr) <= 1e-11 and relmax(df, dfr) <= 1e-10
+    assert relmax(f, fr) <= tol and relmax(df, dfr) <= tol
     m5, A = vs.moments(p)
     m5r = oracle.vmoments(v, a, b, nknots, k, coef)
-    assert np.allclose(m5, m5r, rtol=1e-10, atol=1e-9 * np.max(np.abs(m5r)))
+    assert np.max(np.abs(m5 - m5r)) <= tol * np.max(np.abs(m5r))
     for cons in (False, True):
         vdot = vs.lb_rhs(p, 1.3, cons)
         ref, _, Aref = oracle.lb_rhs(v, w, a, b, nknots, k, M, 1.3, cons)
-        assert relmax(vdot, ref) <= 1e-9, (cons,)
+        assert relmax(vdot, ref) <= tol, (cons,)
         if cons and k >= 3:
-            assert np.allclose(A, Aref, rtol=1e-8)
+            assert np.allclose(A, Aref, rtol=10 * tol)
 
 
 def test_clb_rk438_matches_oracle_and_conserves(vm, oracle, ctx, rng):

@@ -281,11 +281,12 @@ def test_vspace_quantities_at_north_star_tolerance(vm, oracle, ctx, rng, nknots,
         if cons:
             e["A"] = float(np.max(np.abs(np.asarray(A) - np.asarray(Aref)) / np.max(np.abs(Aref))))
     report(f"v-space nknots={nknots} order={k}", **e)
-    # measured on B200 (round 2): every entry between 1e-16 and 4e-13 for these bases; the north star's 1e-12
+    # measured on B200 (round 2, gpurun_out r02a): every entry between 1.2e-16 and 2.1e-14 for these bases
+    # (worst: f' and the CLB right-hand side at 129 knots); asserted at the north star's 1e-12
     assert e["rhs"] <= RTOL and e["coef"] <= RTOL and e["f"] <= RTOL
     assert e["df"] <= 1e-12 and e["m5"] <= 1e-12
     assert e["vdot_lb"] <= 1e-12 and e["vdot_clb"] <= 1e-12
-    assert e["A"] <= 1e-11                                  # ratio of O(N) sums with cancellation in the numerator
+    assert e["A"] <= 1e-12
 
 
 # ------------------------------------------- full-length script histories ----
@@ -317,8 +318,8 @@ def test_config1_vlasov_poisson_script_full_length(vm, oracle, ctx):
     ex, ev = np.max(np.abs(xg - xo)), np.max(np.abs(vg - vo))
     eh = np.max(np.abs(hist_g - hist_o), axis=0) / np.max(np.abs(hist_o), axis=0)
     report("config 1, 200 Strang steps", dx=ex, dv=ev, W=eh[0], K=eh[1], M=eh[2])
-    assert ex <= 1e-9 and ev <= 1e-9            # measured 2e-12 / 4e-12 (rounding differences grow along trajectories)
-    assert np.all(eh <= 1e-10)
+    assert ex <= 2e-12 and ev <= 1e-12          # measured 7.1e-14 / 9.8e-15 (rounding differences grow along trajectories)
+    assert np.all(eh <= 1e-12)                  # measured W 1.9e-14, K 4e-16, M 9e-16
 
 
 def test_config2_bump_on_tail_script_full_length(vm, oracle, ctx):
@@ -340,8 +341,9 @@ def test_config2_bump_on_tail_script_full_length(vm, oracle, ctx):
     eh = np.max(np.abs(diag[:, :3] - dref), axis=0) / np.max(np.abs(dref), axis=0)
     report("config 2, 500 leapfrog steps", dx=ex, dv=ev, W=eh[0], K=eh[1], M=eh[2])
     assert diag.shape == (nt // nsave + 1, 4)
-    assert ex <= 1e-8 and ev <= 1e-8            # measured ~1e-11 (t = 50: trajectories are weakly chaotic)
-    assert eh[0] <= 1e-9 and eh[1] <= 1e-11 and eh[2] <= 1e-11
+    assert ex <= 1e-8 and ev <= 3e-9            # measured 2.5e-10 / 6.1e-11 (t = 50: trajectories are weakly chaotic,
+    #                                             the bump-on-tail instability amplifies rounding differences)
+    assert eh[0] <= 3e-12 and eh[1] <= 1e-12 and eh[2] <= 1e-12      # measured W 7.1e-14, K 3.2e-15, M 3.7e-16
     etot = diag[:, 0] + diag[:, 1]
     assert abs(etot[-1] - etot[0]) / etot[0] <= 1e-3
 
@@ -372,8 +374,8 @@ def test_config4_conservative_lb_long_run(vm, oracle, ctx):
     e2 = np.max(np.abs(diag[:, 2] - rows[:, 1])) / np.max(rows[:, 1])
     report("config 4, 2000 RK438 steps", dv=ev, sum_v=e1, sum_v2=e2)
     assert diag.shape == (nt // every + 1, 4) and np.allclose(diag[:, 0], dt * every * np.arange(nt // every + 1))
-    assert ev <= 1e-9                           # measured ~1e-12
-    assert e1 <= 1e-12 and e2 <= 1e-12
+    assert ev <= 1e-12                          # measured 4.0e-15
+    assert e1 <= 1e-13 and e2 <= 1e-13          # measured 3.4e-16 / 1.8e-16
     # what the script prints (:64): relative momentum / energy drift of the conservative operator
     assert abs(diag[-1, 1] - diag[0, 1]) / npart <= 1e-6 and abs(diag[-1, 2] - diag[0, 2]) / diag[0, 2] <= 1e-6
 
