@@ -73,6 +73,7 @@ int vm_ctx_device_info(vm_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor,
  *      "pairs" (0 = auto, 1, 2, 4, 8): pairs of particles in flight per thread in the lane-private passes;
  *      "priv_min_warps" (0 = auto): fewest warps per SM for which the lane-private deposit is still chosen;
  *      "no_repg" (1: single field table in the fused pass instead of 16 bank-conflict-free copies);
+ *      "bankq" (bank-sorted large-mesh pass: 0 = auto, from 256 cells; 1 = always; -1 = never);
  *      "force_match" (1: MATCH.ANY grouping instead of xor-shuffle rounds), "no_uniform_w" (1: always stream the
  *      weight array), "no_pdl" (1: no programmatic dependent launch), "no_fuse" (1: separate reduce / solve kernels);
  *      "profile" (see vm_profile_read). */
@@ -185,7 +186,7 @@ int vm_deposit(vm_field* f, vm_particles* p, int mode);
  * opt-in shared memory per CTA (B200: 148, 232448).  pass: 0 = deposit only (vm_deposit), 1 = fused
  * kick+drift+deposit step (vm_vp_run), 2 = drift+deposit prologue. */
 typedef struct vm_pass_plan {
-    int variant;        /* 0 lane-private replicas, 1 MATCH.ANY grouping, 2 shared atomics, 3 xor-shuffle */
+    int variant;        /* 0 lane-private replicas, 1 MATCH.ANY grouping, 2 shared atomics, 3 xor-shuffle, 4 bank-sorted queues */
     int replicas;       /* replica grids per warp (per CTA for variant 2) */
     int grid, threads;  /* CTAs, threads per CTA */
     int pairs;          /* pairs of particles in flight per thread */

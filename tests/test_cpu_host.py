@@ -133,6 +133,12 @@ def test_pass_plans_fit_the_device_for_every_mesh_size(vm, order):
             grids = rows * p.replicas * 8 * (1 if p.variant == 2 else warps)
             table = (n + order) * 8 * p.gather_copies if pass_ == 1 else 0
             assert p.smem_bytes >= grids + table + p.threads * 8, what
+            if p.variant == 4:                # bank-sorted pass: one replica per warp + 32 class queues of 16 words per warp
+                assert p.replicas == 1 and ctas == 1 and p.pairs == 1 and warps >= 4, what
+                assert p.smem_bytes >= grids + table + p.threads * 8 + warps * 32 * 16 * 8, what
+                assert p.gather_copies in (1, 2, 4, 8, 16) and (pass_ == 1 or p.gather_copies == 1), what
+                assert p.max_threads == (512 if warps <= 16 else 1024), what
+                continue
             if p.variant == 0:
                 assert p.replicas == 32 and warps >= 6, what
             if p.variant == 3:
@@ -158,7 +164,7 @@ def test_pass_plans_of_the_benchmarked_meshes(vm):
     assert (p.variant, p.grid, p.threads, p.pairs, p.max_threads, p.gather_copies) == (0, 148, 192, 8, 192, 16)
     p = L.pass_plan(128, 4, 0)
     assert (p.variant, p.threads, p.pairs, p.max_threads) == (0, 192, 8, 256)
-    assert L.pass_plan(256, 4, 1).variant == 1 and L.pass_plan(1024, 4, 1).variant == 1
+    assert L.pass_plan(256, 4, 1).variant == 4 and L.pass_plan(1024, 4, 1).variant == 4      # bank-sorted queues
     assert L.pass_plan(16, 4, 0, 1).variant == 2          # VM_DEPOSIT_ATOMIC: the warp-aggregated A/B variant
     for bad in ((0, 4, 1), (16, 7, 1), (16, 4, 3), (5000, 4, 1)):
         with pytest.raises(vm.VMError):

@@ -280,6 +280,7 @@ int vm_ctx_set_tuning(vm_ctx* ctx, const char* key, int value)
         VM_REQUIRE(value >= 0 && value <= 32, "priv_min_warps out of range");
         ctx->priv_min_warps = value;
     }
+    else if (k == "bankq") { VM_REQUIRE(value >= -1 && value <= 1, "bankq must be -1, 0 or 1"); ctx->bankq = value; }
     else if (k == "no_repg") ctx->no_repg = value;   // 1: single (bank-conflicting) gather table in the fused pass (A/B)
     else if (k == "profile") ctx->profile = value;
     else if (k == "force_match") ctx->force_match = value;   // 1: MATCH.ANY grouping instead of xor rounds (A/B)

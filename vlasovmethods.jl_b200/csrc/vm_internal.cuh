@@ -56,6 +56,7 @@ struct vm_ctx {
     cudaEvent_t snap_ready = nullptr, snap_done = nullptr;
     // tuning (0 = auto)
     int ctas_per_sm = 0, threads_per_cta = 0, replicas = 0, profile = 0, no_fuse = 0, no_pdl = 0, force_match = 0, no_uniform_w = 0;
+    int bankq = 0;      // bank-sorted large-mesh pass: 0 = auto (n >= 256), 1 = always, -1 = never
     int pairs = 0, priv_min_warps = 0, no_repg = 0;   // pairs in flight per thread / fewest warps the lane-private deposit accepts
     // per-launch event brackets of the dominant kernel (profile == 1)
     std::vector<cudaEvent_t> prof_events;   // pairs: [2i] start, [2i+1] stop

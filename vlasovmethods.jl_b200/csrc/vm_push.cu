@@ -16,6 +16,7 @@
 //   VAR_MATCH   R < 32 replicas per warp: sort-by-cell segmented reduce inside the warp, leader RMW
 //   VAR_ATOMIC  warp-aggregated atomicAdd on a per-CTA grid + global RED flush (A/B reference)
 #include "vm_pass.cuh"
+#include "vm_pass_bq.cuh"
 
 // ------------------------------------------- kick + drift without deposit ---
 template <int K>
@@ -193,8 +194,37 @@ k_rk4_stage(double* __restrict__ x, double* __restrict__ v, const double* __rest
                              const PassParams&, const FinishParams&);
 VM_DECL_PASS(2) VM_DECL_PASS(3) VM_DECL_PASS(4) VM_DECL_PASS(5) VM_DECL_PASS(6)
 #undef VM_DECL_PASS
+#define VM_DECL_PASS_BQ(k)                                                                                           \
+    void vm_launch_pass_bq_k##k(vm_ctx*, int, const BqPlan&, double*, double*, const double*, const double*, double*, \
+                                const PassParams&, const FinishParams&);
+VM_DECL_PASS_BQ(2) VM_DECL_PASS_BQ(3) VM_DECL_PASS_BQ(4) VM_DECL_PASS_BQ(5) VM_DECL_PASS_BQ(6)
+#undef VM_DECL_PASS_BQ
+
+// Meshes from this size on run the bank-sorted pass (vm_pass_bq.cuh); below it lane-private replicas fit with enough
+// warps.  Tuning key "bankq": 0 = this rule (the first size without a lane-private plan), 1 = always (n >= 8), -1 = never (A/B: the round-1 variants).
+#define VM_BQ_MIN_N 129
 
 namespace {
+
+void launch_pass_bq(vm_ctx* ctx, int mode, int order, const BqPlan& bp, double* x, double* v, const double* w,
+                    const double* dcoef, double* out, const PassParams& P, const FinishParams& F)
+{
+    switch (order) {
+        case 2: vm_launch_pass_bq_k2(ctx, mode, bp, x, v, w, dcoef, out, P, F); break;
+        case 3: vm_launch_pass_bq_k3(ctx, mode, bp, x, v, w, dcoef, out, P, F); break;
+        case 4: vm_launch_pass_bq_k4(ctx, mode, bp, x, v, w, dcoef, out, P, F); break;
+        case 5: vm_launch_pass_bq_k5(ctx, mode, bp, x, v, w, dcoef, out, P, F); break;
+        case 6: vm_launch_pass_bq_k6(ctx, mode, bp, x, v, w, dcoef, out, P, F); break;
+        default: throw vm_error(VM_ERR_UNSUPPORTED, "spline order must be in 2..6");
+    }
+}
+
+bool want_bankq(vm_ctx* ctx, int n, int deposit_mode)
+{
+    if (deposit_mode != VM_DEPOSIT_DETERMINISTIC || ctx->bankq < 0) return false;
+    if (ctx->ctas_per_sm > 0 || ctx->threads_per_cta > 0 || ctx->replicas > 0 || ctx->force_match) return false;   // hand-tuned round-1 variants
+    return ctx->bankq > 0 ? n >= 8 : n >= VM_BQ_MIN_N;
+}
 
 void launch_pass(vm_ctx* ctx, int mode, int order, const DepositPlan& pl, double* x, double* v, const double* w,
                  const double* dcoef, double* out, const PassParams& P, const FinishParams& F)
@@ -280,14 +310,21 @@ static void pass_with_deposit(vm_field* f, vm_particles* p, int pass_mode, int d
     vm_ctx* ctx = f->ctx;
     const int n = f->n;
     const int ncols = n;   // partial rows hold the grid only (the K/M sums live in their own rows)
-    const PassPlan pp = plan_pass(ctx, n, f->order, pass_mode, deposit_mode);
-    const DepositPlan& pl = pp.pl;
-    P.repg = pp.repg ? 1 : 0;
     P.map = f->map;
     P.n = p->n;
-    P.rep_log2 = pl.rep_log2;
     P.ncols = ncols;
     P.uw = vm_particles_uniform_weight(p, &P.w0) ? 1 : 0;
+    BqPlan bp{};
+    const bool bq = want_bankq(ctx, n, deposit_mode) && plan_bq(ctx, n, f->order, pass_mode, P.uw != 0, &bp);
+    DepositPlan pl{};
+    if (bq) {          // bank-sorted pass: one CTA per SM, one replica grid per warp
+        pl.var = VAR_MATCH; pl.rep_log2 = 0; pl.grid = ctx->sm_count; pl.threads = bp.warps * 32; pl.smem = bp.smem;
+    } else {
+        const PassPlan pp = plan_pass(ctx, n, f->order, pass_mode, deposit_mode);
+        pl = pp.pl;
+        P.repg = pp.repg ? 1 : 0;
+    }
+    P.rep_log2 = pl.rep_log2;
     FinishParams F{};
     F.mode = FINISH_NONE;
     double* out;
@@ -315,7 +352,8 @@ static void pass_with_deposit(vm_field* f, vm_particles* p, int pass_mode, int d
     // the dominant kernel of its caller: the fused pass inside vm_vp_run, the deposit pass elsewhere
     const bool prof = (pass_mode == MODE_PUSH_DEPOSIT) || (pass_mode == MODE_DEPOSIT && prof_deposit);
     if (prof) vm_prof_mark(ctx);
-    launch_pass(ctx, pass_mode, f->order, pl, xsrc ? xsrc : p->x, p->v, p->w, f->dcoef, out, P, F);
+    if (bq) launch_pass_bq(ctx, pass_mode, f->order, bp, xsrc ? xsrc : p->x, p->v, p->w, f->dcoef, out, P, F);
+    else launch_pass(ctx, pass_mode, f->order, pl, xsrc ? xsrc : p->x, p->v, p->w, f->dcoef, out, P, F);
     if (prof) vm_prof_mark(ctx);
     if (pl.var != VAR_ATOMIC && F.mode == FINISH_NONE) vm_field_reduce_rows(f, out, pl.grid, ncols, f->rhs);
     f->rhs_global = (ctx->nranks == 1) || F.xchg;
@@ -358,6 +396,18 @@ int vm_pass_plan_query(int sm_count, size_t smem_optin_bytes, int n_basis, int o
         dev.sm_count = sm_count;
         dev.smem_optin = smem_optin_bytes;
         const int mode = pass == 0 ? MODE_DEPOSIT : (pass == 1 ? MODE_PUSH_DEPOSIT : MODE_DRIFT_DEPOSIT);
+        BqPlan bp{};
+        if (want_bankq(&dev, n_basis, deposit_mode) && plan_bq(&dev, n_basis, order, mode, true, &bp)) {
+            out->variant = 4;
+            out->replicas = 1;
+            out->grid = sm_count;
+            out->threads = bp.warps * 32;
+            out->pairs = 1;
+            out->max_threads = bp.warps <= 16 ? 512 : 1024;
+            out->gather_copies = mode == MODE_PUSH_DEPOSIT ? (1 << bp.gshift) : 1;
+            out->smem_bytes = bp.smem;
+            return VM_OK;
+        }
         const PassPlan pp = plan_pass(&dev, n_basis, order, mode, deposit_mode);
         const int per_sm = pp.pl.threads * (pp.pl.grid / sm_count);
         const PassTier t = vm_pass_tier(mode, pp.pl.var, per_sm, 0);
