@@ -8,6 +8,9 @@
 #include "vm_deposit.cuh"
 
 enum { MODE_DEPOSIT = 0, MODE_PUSH_DEPOSIT = 1, MODE_DRIFT_DEPOSIT = 2 };
+#ifndef VM_PASS_EARLY_LOAD
+#define VM_PASS_EARLY_LOAD 0     // 1: first batch of particle loads before griddepcontrol.wait -- measured neutral (8.49 vs 8.43 us fixed cost, profiles/r02_early_load_ab.txt), off
+#endif
 
 struct PassParams {
     CellMap map;
@@ -122,11 +125,6 @@ k_vp_pass(double* __restrict__ x, double* __restrict__ v, const double* __restri
     const int gtotal = (VAR == VAR_ATOMIC) ? gsz : gsz * nwarps;
     double* scratch = grid + gtotal;
     for (int i = threadIdx.x; i < gtotal; i += blockDim.x) grid[i] = 0.0;
-    // Programmatic dependent launch: everything above overlaps the previous kernel's tail (its last
-    // CTA is still reducing / exchanging / solving); nothing it wrote is read before this point.
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    if (MODE == MODE_PUSH_DEPOSIT) load_dcoef_ext<REPG>(dsh, dcoef, n, K - 2 > 0 ? K - 2 : 0);
-    __syncthreads();
     double* wg = (VAR == VAR_ATOMIC) ? grid : grid + warp * gsz;
     const int rep = ((VAR == VAR_ATOMIC) ? warp : lane) & ((1 << P.rep_log2) - 1);
 
@@ -197,7 +195,16 @@ k_vp_pass(double* __restrict__ x, double* __restrict__ v, const double* __restri
     for (int u = 0; u < U; ++u) A[u].x = A[u].v = B[u].x = B[u].v = make_double2(0., 0.);
     // q advances by `chunk` per iteration; npairs + 3*chunk < 2^32 is guaranteed by vm_particles_create
     unsigned q = gtid;
-    load(A, q);
+    // Programmatic dependent launch: the replica zero-fill above and the first batch of particle loads below overlap
+    // the previous kernel's tail (its last CTA is still reducing / exchanging / solving).  The particle arrays are
+    // safe to read early: a pass kernel fences its stores before griddepcontrol.launch_dependents, and this grid only
+    // starts once every CTA of the previous one has passed that point (any other kind of predecessor runs to
+    // completion first).  What the finish of the previous kernel writes (dcoef) is read after griddepcontrol.wait.
+    if (MODE == MODE_PUSH_DEPOSIT && VM_PASS_EARLY_LOAD) load(A, q);
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (MODE == MODE_PUSH_DEPOSIT) load_dcoef_ext<REPG>(dsh, dcoef, n, K - 2 > 0 ? K - 2 : 0);
+    __syncthreads();
+    if (!(MODE == MODE_PUSH_DEPOSIT && VM_PASS_EARLY_LOAD)) load(A, q);
     if (MODE == MODE_DEPOSIT) {
         // 16 B/particle pass, issue-bound: unrolled twice over the two buffer sets (no register moves)
         for (unsigned it = 0; it < iters; it += 2, q += 2 * chunk) {
@@ -216,7 +223,9 @@ k_vp_pass(double* __restrict__ x, double* __restrict__ v, const double* __restri
             for (int u = 0; u < U; ++u) A[u] = B[u];
         }
     }
-    // let the next kernel of the stream start its prologue while this grid drains and finishes
+    // let the next kernel of the stream start its prologue while this grid drains and finishes; the fence makes this
+    // thread's particle stores visible before the trigger (the next kernel loads its first batch before its wait)
+    if (MODE != MODE_DEPOSIT && VM_PASS_EARLY_LOAD) __threadfence();
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if ((P.n & 1) && blockIdx.x == 0 && warp == 0) {   // odd particle count: last particle, lane 0 of one warp
         const bool active = (lane == 0);

@@ -289,6 +289,7 @@ k_vp_pass_bq(double* __restrict__ x, double* __restrict__ v, const double* __res
         load(A, q + 2 * stride);
         work(B, q + stride);                                   // all-inactive when iters is odd (one idle half-iteration)
     }
+    if (MODE != MODE_DEPOSIT && VM_PASS_EARLY_LOAD) __threadfence();     // same protocol as k_vp_pass: stores visible before the trigger
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if ((P.n & 1) && blockIdx.x == 0 && warp == 0) {           // odd particle count: last particle, lane 0 of one warp
         const bool active = (lane == 0);
