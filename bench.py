@@ -273,6 +273,26 @@ def parity_check(vm, ctx, rank, world, dist):
         out["max_rel"] = max(out["max_rel"], err)
         out["ranks_bitwise"] = bool(out["ranks_bitwise"] and same)
         fld.close()
+    # order-independent fixed-point deposit (VM_DEPOSIT_FIXED): the sharded run must have the BITS of a one-GPU run of
+    # the whole problem (rank 0 repeats it alone on a context without communicator)
+    if world == 1 or ctx.peer_connected():
+        fld = vm.DeviceField(ctx, a, b, k, 16, 0)
+        p.upload(x[lo:hi], v[lo:hi], w[lo:hi])
+        fld.run(p, dt, 4, 0, vm._lib.VM_RUN_FIXED_DEPOSIT, 1.0)
+        phis = fld.coefficients.copy()
+        solo = vm.Context(ctx.device)
+        f1 = vm.DeviceField(solo, a, b, k, 16, 0)
+        p1 = vm.DeviceParticles(solo, npart)
+        p1.upload(x, v, w)
+        solo.set_tuning("bankq", 1)                # ... and with the other deposit layout
+        f1.run(p1, dt, 4, 0, vm._lib.VM_RUN_FIXED_DEPOSIT, 1.0)
+        same = bool(np.array_equal(f1.coefficients, phis))
+        if world > 1:
+            red = torch.tensor([0.0 if same else 1.0], dtype=torch.float64)
+            dist.all_reduce(red, op=dist.ReduceOp.MAX)
+            same = red[0] == 0.0
+        out["fixed_point_bits_equal_single_gpu_run"] = bool(same)
+        solo.close(); fld.close()
     # v-space: sharded conservative Lenard-Bernstein right-hand side
     vs = vm.DeviceVSpline(ctx, -10.0, 10.0, 41, 4, 1)
     wv = np.full(npart, 1.0 / npart)
@@ -287,7 +307,8 @@ def parity_check(vm, ctx, rank, world, dist):
         e = float(red[0])
     out["clb_rhs_max_rel"] = e
     out["tolerance"] = 1e-10
-    out["ok"] = bool(out["max_rel"] <= 1e-10 and e <= 1e-10 and out["ranks_bitwise"])
+    out["ok"] = bool(out["max_rel"] <= 1e-10 and e <= 1e-10 and out["ranks_bitwise"]
+                     and out.get("fixed_point_bits_equal_single_gpu_run", True))
     vs.close(); p.close()
     return out
 

@@ -174,7 +174,12 @@ typedef enum vm_deposit_mode {
     VM_DEPOSIT_DETERMINISTIC = 0, /* warp-private replicas, in-warp sort-by-cell segmented
                                      reduce in lane order, fixed-order tree across warps/CTAs:
                                      bit-reproducible run to run */
-    VM_DEPOSIT_ATOMIC = 1         /* warp-aggregated shared-memory atomics + global fp64 RED */
+    VM_DEPOSIT_ATOMIC = 1,        /* warp-aggregated shared-memory atomics + global fp64 RED */
+    VM_DEPOSIT_FIXED = 2          /* order-independent: every contribution w B_j(x) is rounded once to a 64-bit
+                                     fixed-point integer (scale 2^S from an exact bound on sum |w|) and all sums --
+                                     replicas, CTAs, GPUs -- are integer sums: identical bits for every launch
+                                     geometry, deposit layout and number of GPUs (SURVEY 8c KAT 10, 8e).  Needs the
+                                     fused finish (n_basis <= 1024) and, across ranks, the peer exchange. */
 } vm_deposit_mode;
 
 /* projection!(potential, dist): src/projections/potential.jl:2-22.
@@ -221,7 +226,9 @@ typedef enum vm_run_flags {
     VM_RUN_FROZEN_FIELD = 2,  /* field_source = model_ics: never re-deposit; reproduces the
                                  frozen-field quirk of the new API                   */
     VM_RUN_ATOMIC_DEPOSIT = 4,/* use VM_DEPOSIT_ATOMIC inside the fused step                     */
-    VM_RUN_UNFUSED = 8        /* separate drift / deposit / solve / kick passes (for A/B tests)  */
+    VM_RUN_UNFUSED = 8,       /* separate drift / deposit / solve / kick passes (for A/B tests)  */
+    VM_RUN_FIXED_DEPOSIT = 16 /* use VM_DEPOSIT_FIXED inside the step: the whole run is bit-identical for
+                                 every launch geometry and GPU count                              */
 } vm_run_flags;
 
 /* nsteps Strang steps A(dt/2) B(dt) A(dt/2) with self-consistent field:

@@ -52,6 +52,22 @@ for n in (32, 200, 1024):          # one-level fused finish, two-level finish (+
     rhs_all = orc.deposit_periodic(xo, w, a, b, n, k, 0)
     assert np.max(np.abs(phi2 - orc.poisson_solve(S, rhs_all))) <= 1e-10 * np.max(np.abs(phi2))
     fld.close()
+# order-independent fixed-point deposit: the sharded run has the bits of the single-GPU run of the whole problem
+if ctx.peer_connected():
+    for n in (16, 256):
+        fld = vm.DeviceField(ctx, a, b, k, n, 0)
+        p.upload(x[lo:hi], v[lo:hi], w[lo:hi])
+        fld.run(p, dt, 4, 0, vm._lib.VM_RUN_FIXED_DEPOSIT, 1.0)
+        xs = p.download(w=False)[0]
+        phis = fld.coefficients.copy()
+        solo = vm.Context(ctx.device)                 # no communicator: this rank alone, all particles
+        f1 = vm.DeviceField(solo, a, b, k, n, 0)
+        p1 = vm.DeviceParticles(solo, npart)
+        p1.upload(x, v, w)
+        f1.run(p1, dt, 4, 0, vm._lib.VM_RUN_FIXED_DEPOSIT, 1.0)
+        assert np.array_equal(f1.coefficients, phis), ("fixed-point phi differs between 1 and %d GPUs" % world, n)
+        assert np.array_equal(p1.download(w=False)[0][lo:hi], xs), ("fixed-point trajectories differ", n)
+        solo.close(); fld.close()
 # a rank with an EMPTY shard takes part in every exchange (one particle over `world` ranks)
 n = 16
 small = 1

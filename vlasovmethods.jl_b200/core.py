@@ -95,6 +95,10 @@ class Context:
         """handles: nranks x 64 bytes in rank order (all-gathered peer_handle() results)."""
         buf = C.create_string_buffer(handles, len(handles))
         L.check(L.lib().vm_ctx_peer_connect(self._h, buf), self._h)
+        self._peer_connected = True
+
+    def peer_connected(self) -> bool:
+        return bool(getattr(self, "_peer_connected", False))
 
     def comm_info(self):
         r, n = C.c_int(), C.c_int()

@@ -153,6 +153,14 @@ void vm_allreduce_sum(vm_ctx* ctx, double* dev, size_t count)
     nccl_check(api, api.AllReduce(dev, dev, count, ncclDouble, ncclSum, ctx->nccl_comm, ctx->stream), "ncclAllReduce");
 }
 
+void vm_allreduce_max(vm_ctx* ctx, double* dev, size_t count)
+{
+    if (ctx->nranks <= 1) return;
+    NcclApi& api = nccl_api();
+    const int ncclDouble = 8, ncclMax = 2;
+    nccl_check(api, api.AllReduce(dev, dev, count, ncclDouble, ncclMax, ctx->nccl_comm, ctx->stream), "ncclAllReduce(max)");
+}
+
 // ------------------------------------------------------------------- API ----
 extern "C" {
 
@@ -465,6 +473,28 @@ __global__ void __launch_bounds__(256) k_fill_const(double* __restrict__ a, long
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) a[i] = c;
 }
 
+// out[0] = max |w| (bit pattern of a non-negative double orders like an integer: atomicMax is exact and order-free)
+__global__ void __launch_bounds__(256) k_wabs_max(const double* __restrict__ w, long n, unsigned long long* __restrict__ out)
+{
+    double m = 0.0;
+    const long stride = (long)gridDim.x * blockDim.x;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) m = fmax(m, fabs(w[i]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(VM_FULL_MASK, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(out, (unsigned long long)__double_as_longlong(m));
+}
+
+// out[0] += sum_p floor(|w_p| * q): integer sum -- exact, so independent of the order and of the sharding
+__global__ void __launch_bounds__(256) k_wabs_qsum(const double* __restrict__ w, long n, double q, unsigned long long* __restrict__ out)
+{
+    unsigned long long s = 0ull;
+    const long stride = (long)gridDim.x * blockDim.x;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) s += (unsigned long long)(fabs(w[i]) * q);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(VM_FULL_MASK, s, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(out, s);
+}
+
 // Host <-> device transfers of big arrays go through a pair of pinned bounce buffers so that
 // pageable host memory (a Julia Array) still streams at PCIe rate and overlaps with the copy engine.
 void copy_h2d(vm_ctx* ctx, double* dst, const double* src, size_t n)
@@ -501,6 +531,55 @@ bool vm_particles_uniform_weight(vm_particles* p, double* w0)
     }
     if (w0) *w0 = p->w0;
     return p->uniform_w;
+}
+
+// Scale exponent S of the fixed-point deposit: every |w_p| B_j is rounded to a multiple of 2^-S and summed as a 64-bit
+// integer.  S must be the same on every rank and for every sharding of the same particles, so it is derived from
+// quantities that are EXACT: max |w| (a maximum), sum_p floor(|w_p| 2^20 / max|w|) (an integer sum below 2^53) and the
+// particle count.  U = (qsum + N) max|w| 2^-20 >= sum |w| bounds every row sum; S = min(60 - ilogb(U), 50 - ilogb(max|w|))
+// keeps row sums below 2^62 and single contributions below 2^51 (the magic-number rounding of fix_of).
+int vm_particles_fixed_scale(vm_particles* p)
+{
+    vm_ctx* ctx = p->ctx;
+    if (!p->fix_dirty && p->fix_nranks == ctx->nranks) return p->fix_S;
+    double* d = vm_partials(ctx, 8);                       // [0] max bits / max, [1] qsum, [2] n
+    double* host = vm_pinned(ctx, 8);
+    VM_CUDA(cudaMemsetAsync(d, 0, 8 * sizeof(double), ctx->stream));
+    if (p->n > 0) {
+        k_wabs_max<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(p->w, p->n, (unsigned long long*)d);
+        ++ctx->launches;
+    }
+    vm_allreduce_max(ctx, d, 1);                           // (the bit pattern of a non-negative double IS the double)
+    VM_CUDA(cudaMemcpyAsync(host, d, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    VM_CUDA(cudaStreamSynchronize(ctx->stream));
+    const double wmax = host[0];
+    int S = 0;
+    if (wmax > 0.0 && wmax < 1e300) {
+        const double q = 1048576.0 / wmax;
+        VM_CUDA(cudaMemsetAsync(d + 1, 0, sizeof(double), ctx->stream));
+        if (p->n > 0) {
+            k_wabs_qsum<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(p->w, p->n, q, (unsigned long long*)(d + 1));
+            ++ctx->launches;
+        }
+        unsigned long long qs = 0ull;
+        VM_CUDA(cudaMemcpyAsync(&qs, d + 1, sizeof(qs), cudaMemcpyDeviceToHost, ctx->stream));
+        VM_CUDA(cudaStreamSynchronize(ctx->stream));
+        host[1] = (double)qs;                              // < 2^33 * 2^20 = 2^53: exact
+        host[2] = (double)p->n;
+        VM_CUDA(cudaMemcpyAsync(d + 1, host + 1, 2 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        vm_allreduce_sum(ctx, d + 1, 2);                   // integers below 2^53: exact in any order
+        VM_CUDA(cudaMemcpyAsync(host + 1, d + 1, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        VM_CUDA(cudaStreamSynchronize(ctx->stream));
+        const double U = (host[1] + host[2]) * wmax * (1.0 / 1048576.0);
+        const int s_sum = 60 - ilogb(U), s_one = 50 - ilogb(wmax);
+        S = s_sum < s_one ? s_sum : s_one;
+        if (S > 1000) S = 1000;
+        if (S < -1000) S = -1000;
+    }
+    p->fix_S = S;
+    p->fix_dirty = false;
+    p->fix_nranks = ctx->nranks;
+    return S;
 }
 
 extern "C" {
@@ -554,7 +633,7 @@ int vm_particles_upload_soa(vm_particles* p, const double* x, const double* v, c
     if (p->n > 0) {
         if (x) copy_h2d(p->ctx, p->x, x, (size_t)p->n);
         if (v) copy_h2d(p->ctx, p->v, v, (size_t)p->n);
-        if (w) { copy_h2d(p->ctx, p->w, w, (size_t)p->n); p->w_dirty = true; }
+        if (w) { copy_h2d(p->ctx, p->w, w, (size_t)p->n); p->w_dirty = true; p->fix_dirty = true; }
         VM_CUDA(cudaStreamSynchronize(p->ctx->stream));   // host buffers are only borrowed for the call
     }
     VM_API_END
@@ -588,6 +667,7 @@ int vm_particles_set_uniform_weight(vm_particles* p, double w0)
     p->uniform_w = true;
     p->w0 = w0;
     p->w_dirty = false;
+    p->fix_dirty = true;
     VM_API_END
 }
 
@@ -598,6 +678,7 @@ int vm_particles_upload_aos(vm_particles* p, const double* z)
     if (p->n > 0) {
         vm_ctx* ctx = p->ctx;
         p->w_dirty = true;
+        p->fix_dirty = true;
         // stage in chunks through the scratch buffer to bound the extra device memory
         const long chunk = 1L << 22;   // particles per chunk (96 MiB of AoS)
         double* stage = vm_partials(ctx, (size_t)3 * (size_t)(p->n < chunk ? p->n : chunk));
@@ -702,6 +783,7 @@ int vm_particles_copy(vm_particles* dst, vm_particles* src)
         VM_CUDA(cudaMemcpyAsync(dst->w, src->w, bytes, cudaMemcpyDeviceToDevice, dst->ctx->stream));
     }
     dst->w_dirty = true;
+    dst->fix_dirty = true;
     VM_API_END
 }
 

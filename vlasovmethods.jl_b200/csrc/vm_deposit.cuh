@@ -10,21 +10,48 @@
 
 enum { VAR_PRIV = 0, VAR_MATCH = 1, VAR_ATOMIC = 2, VAR_XOR = 3 };
 
+// ------------------------------------------------ order-independent sums -----
+// VM_DEPOSIT_FIXED: every contribution w * B_j(xi) is rounded ONCE to a 64-bit fixed-point integer (scale 2^S, S
+// from an exact, sharding-independent bound on sum |w|) and all further additions -- replica grids, CTA rows, ranks --
+// are integer additions, which commute: the deposited vector has the same bits for every launch geometry, deposit
+// layout and number of GPUs.  The accumulators live in the same 8-byte words as the fp64 ones (bit patterns).
+#define VM_FIX_MAGIC 6755399441055744.0      // 1.5 * 2^52: fma(v, scale, MAGIC) holds rint(v * scale) in its low mantissa bits
+__device__ __forceinline__ long long fix_of(double v, double scale)          // |v * scale| < 2^51
+{
+    return __double_as_longlong(fma(v, scale, VM_FIX_MAGIC)) - __double_as_longlong(VM_FIX_MAGIC);
+}
+template <bool FIXED>
+__device__ __forceinline__ double acc_add(double a, double b)
+{
+    return FIXED ? __longlong_as_double(__double_as_longlong(a) + __double_as_longlong(b)) : a + b;
+}
+__device__ __forceinline__ double acc_add_rt(double a, double b, int fixed)
+{
+    return fixed ? __longlong_as_double(__double_as_longlong(a) + __double_as_longlong(b)) : a + b;
+}
+
 // ---------------------------------------------------------------- scatter ---
 // Replica grids carry `ghost` extra rows after the n real ones, so a particle's K consecutive
 // basis indices b0 .. b0+K-1 never wrap inside the hot loop (periodic grids: ghost = K-1, folded back
 // onto rows 0..K-2 when the grid is flushed; clamped v-space grids: ghost = 0).
 //
 // Add val[j] to row b0 + j, j < K, in this warp's replica grid.  Inactive lanes must carry val == 0.
-template <int K, int VAR>
+template <int K, int VAR, bool FIXED = false>
 __device__ __forceinline__ void scatter(double* __restrict__ wg, int rep_log2, int rep, int lane,
-                                        int b0, const double (&val)[K], bool active)
+                                        int b0, const double (&val)[K], bool active, double fixscale = 0.0)
 {
+    static_assert(!FIXED || VAR == VAR_PRIV, "fixed-point accumulation exists in the lane-private and bank-sorted layouts");
     if (VAR == VAR_PRIV) {
         // one private column per lane: no collisions, no branches, immediate-offset LDS/DADD/STS
-        double* a = wg + (b0 << 5) + lane;
+        if (FIXED) {
+            long long* a = (long long*)wg + (b0 << 5) + lane;
 #pragma unroll
-        for (int j = 0; j < K; ++j) a[j * 32] += val[j];
+            for (int j = 0; j < K; ++j) a[j * 32] += fix_of(val[j], fixscale);
+        } else {
+            double* a = wg + (b0 << 5) + lane;
+#pragma unroll
+            for (int j = 0; j < K; ++j) a[j * 32] += val[j];
+        }
         return;
     }
     if (VAR == VAR_XOR) {
@@ -98,7 +125,7 @@ __device__ __forceinline__ void scatter(double* __restrict__ wg, int rep_log2, i
 //   phase 1  element-wise sum of the per-warp grids into warp 0's grid (consecutive threads, consecutive words)
 //   phase 2  one warp per group of 32/R rows: lanes read 32 consecutive words and the R replicas of each row
 //            are combined with a segmented xor butterfly
-template <int VAR>
+template <int VAR, bool FIXED = false>
 __device__ __forceinline__ void flush_grid(double* __restrict__ grid, double* __restrict__ scratch,
                                            double* __restrict__ out, int n, int ghost, int rep_log2, int nwarps,
                                            int ncols)
@@ -111,7 +138,7 @@ __device__ __forceinline__ void flush_grid(double* __restrict__ grid, double* __
     if (VAR != VAR_ATOMIC) {                       // phase 1 (the atomic variant has a single per-CTA grid)
         for (int e = t; e < gsz; e += T) {
             double s = grid[e];
-            for (int wq = 1; wq < nwarps; ++wq) s += grid[wq * gsz + e];
+            for (int wq = 1; wq < nwarps; ++wq) s = acc_add<FIXED>(s, grid[wq * gsz + e]);
             grid[e] = s;
         }
         __syncthreads();
@@ -123,7 +150,7 @@ __device__ __forceinline__ void flush_grid(double* __restrict__ grid, double* __
         for (int g = warp * rows_per_warp; g < chunk_rows; g += (T >> 5) * rows_per_warp) {
             const int row = base + g + (lane >> rep_log2);
             double s = (g + (lane >> rep_log2) < chunk_rows) ? grid[((base + g) << rep_log2) + lane] : 0.0;
-            for (int o = R >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(VM_FULL_MASK, s, o);
+            for (int o = R >> 1; o > 0; o >>= 1) s = acc_add<FIXED>(s, __shfl_xor_sync(VM_FULL_MASK, s, o));
             if ((lane & (R - 1)) == 0 && g + (lane >> rep_log2) < chunk_rows) scratch[row - base] = s;
         }
         __syncthreads();
@@ -136,10 +163,10 @@ __device__ __forceinline__ void flush_grid(double* __restrict__ grid, double* __
                 double gsum;
                 if (gr >= base && gr < base + chunk_rows) gsum = scratch[gr - base];
                 else {
-                    gsum = 0.0;
-                    for (int r = 0; r < R; ++r) gsum += grid[(gr << rep_log2) + r];
+                    gsum = 0.0;        // (all-zero bits: also the fixed-point zero)
+                    for (int r = 0; r < R; ++r) gsum = acc_add<FIXED>(gsum, grid[(gr << rep_log2) + r]);
                 }
-                s += gsum;
+                s = acc_add<FIXED>(s, gsum);
             }
             if (VAR == VAR_ATOMIC) atomicAdd(out + i, s);
             else out[(size_t)blockIdx.x * ncols + i] = s;
@@ -180,6 +207,8 @@ struct FinishParams {
     double* dcoef;          // n
     double inv_h;
     // xchg: all-gather of the partial grids through NVLink peer memory ("LL" words: data + sequence number)
+    int fixed;              // the rows hold 64-bit fixed-point integers (VM_DEPOSIT_FIXED): integer sums, converted at the end
+    double inv_scale;       // 2^-S
     int xchg, nranks, rank;
     unsigned long long seq;             // exchange number (identical on all ranks); slot set = seq & 1
     unsigned long long* peer[VM_MAX_PEERS];   // every rank's inbox as mapped on this device (peer[rank] is this rank's own)
@@ -229,7 +258,8 @@ __device__ __forceinline__ void exchange_ll(const FinishParams& F, double* __res
         double s = 0.0;
 #pragma unroll
         for (int r = 0; r < VM_MAX_PEERS; ++r)
-            if (r < F.nranks) s += __longlong_as_double((long long)((lo[r] & 0xffffffffull) | (hi[r] << 32)));
+            if (r < F.nranks) s = acc_add_rt(s, __longlong_as_double((long long)((lo[r] & 0xffffffffull) | (hi[r] << 32))), F.fixed);
+        if (F.fixed) s = (double)__double_as_longlong(s) * F.inv_scale;     // the one conversion back to fp64
         v[i] = s;
         gout[i] = s;
     }
@@ -322,15 +352,18 @@ __device__ __forceinline__ void finish_last_cta(const FinishParams& F, const dou
                 vals[u] = (rr < nrows) ? __ldcg(rows + (size_t)rr * n + i) : 0.0;
             }
 #pragma unroll
-            for (int u = 0; u < 8; ++u) s += vals[u];
+            for (int u = 0; u < 8; ++u) s = acc_add_rt(s, vals[u], F.fixed);
         }
         scratch[part * n + i] = s;
     }
     __syncthreads();
     if (t < n) {
         double s = 0.0;
-        for (int part = 0; part < P; ++part) s += scratch[part * n + t];
-        if (!F.xchg) F.rhs[t] = s;
+        for (int part = 0; part < P; ++part) s = acc_add_rt(s, scratch[part * n + t], F.fixed);
+        if (!F.xchg) {
+            if (F.fixed) s = (double)__double_as_longlong(s) * F.inv_scale;
+            F.rhs[t] = s;
+        }
         r_sh[t] = s;
     }
     if (F.xchg) exchange_ll(F, r_sh, n, F.rhs);
@@ -358,7 +391,7 @@ __device__ __forceinline__ void finish_two_level(const FinishParams& F, const do
         for (int u = 0; u < VM_GROUP_CTAS; ++u) vals[u] = (u < cnt) ? __ldcg(rows + (size_t)(r0 + u) * n + i) : 0.0;
         double s = 0.0;
 #pragma unroll
-        for (int u = 0; u < VM_GROUP_CTAS; ++u) s += vals[u];
+        for (int u = 0; u < VM_GROUP_CTAS; ++u) s = acc_add_rt(s, vals[u], F.fixed);
         F.grows[(size_t)g * n + i] = s;
     }
     __threadfence();
@@ -377,9 +410,12 @@ __device__ __forceinline__ void finish_two_level(const FinishParams& F, const do
 #pragma unroll
             for (int u = 0; u < 8; ++u) vals[u] = (q0 + u < ngroups) ? __ldcg(F.grows + (size_t)(q0 + u) * n + i) : 0.0;
 #pragma unroll
-            for (int u = 0; u < 8; ++u) s += vals[u];
+            for (int u = 0; u < 8; ++u) s = acc_add_rt(s, vals[u], F.fixed);
         }
-        if (!F.xchg) F.rhs[i] = s;
+        if (!F.xchg) {
+            if (F.fixed) s = (double)__double_as_longlong(s) * F.inv_scale;
+            F.rhs[i] = s;
+        }
         sm_a[i] = s;
     }
     if (F.xchg) exchange_ll(F, sm_a, n, F.rhs);

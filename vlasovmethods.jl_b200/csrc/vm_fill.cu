@@ -163,6 +163,7 @@ extern "C" int vm_particles_fill(vm_particles* p, int kind, const double* params
         k_fill<<<grid, 256, 0, ctx->stream>>>(P, p->x, p->v, p->w);
         VM_LAUNCHED(ctx);
         p->w_dirty = true;
+        p->fix_dirty = true;
     }
     VM_API_END
 }

@@ -93,6 +93,10 @@ struct vm_particles {
     bool w_dirty = true;        // w changed since the last classification
     bool uniform_w = false;
     double w0 = 0.0;
+    // fixed-point scale of VM_DEPOSIT_FIXED (vm_particles_fixed_scale): valid until the weights or the communicator change
+    bool fix_dirty = true;
+    int fix_S = 0;
+    int fix_nranks = 0;
 };
 
 // Map a position to (first basis index, xi) on a uniform periodic grid.
@@ -152,6 +156,8 @@ void vm_child_quiesce(vm_ctx* ctx, int device);   // device idle for this child:
 double* vm_partials(vm_ctx* ctx, size_t elems);   // grow-only device scratch
 double* vm_pinned(vm_ctx* ctx, size_t elems);     // grow-only pinned host scratch
 void vm_allreduce_sum(vm_ctx* ctx, double* dev, size_t count);  // no-op when nranks == 1
+void vm_allreduce_max(vm_ctx* ctx, double* dev, size_t count);  // no-op when nranks == 1
+int vm_particles_fixed_scale(vm_particles* p);                  // S of VM_DEPOSIT_FIXED: contributions are rounded to multiples of 2^-S
 void vm_launch_geometry(vm_ctx* ctx, int* grid, int* threads);
 void vm_prof_mark(vm_ctx* ctx);
 void vm_check_peer_error(vm_ctx* ctx);

@@ -24,6 +24,7 @@ struct PassParams {
     int uw;                   // all particles carry the weight w0: the weight array is not read
     int repg;                 // fused pass: the gather table is stored VM_GATHER_COPIES times (conflict-free reads)
     double w0;
+    double fixscale;          // VM_DEPOSIT_FIXED: 2^S (contributions are accumulated as 64-bit integers); 0: fp64 accumulation
 };
 
 // ---------------------------------------------------------------- gather ----
@@ -89,14 +90,14 @@ __device__ __forceinline__ void prepare(double& xp, double& vp, double wp, const
     bspline_uniform_w<K>(xi, wp, val);                 // inactive lanes carry wp == 0
 }
 
-template <int K, int VAR, int MODE, bool SPLIT, bool POW2, bool REPG>
+template <int K, int VAR, int MODE, bool SPLIT, bool POW2, bool REPG, bool FIXED = false>
 __device__ __forceinline__ void process(double& xp, double& vp, double wp, bool active, const PassParams& P,
                                         const double* __restrict__ dsh, double* __restrict__ wg, int rep, int lane)
 {
     int b0;
     double val[K];
     prepare<K, MODE, SPLIT, POW2, REPG>(xp, vp, wp, P, dsh, b0, val);
-    scatter<K, VAR>(wg, P.rep_log2, rep, lane, b0, val, active);
+    scatter<K, VAR, FIXED>(wg, P.rep_log2, rep, lane, b0, val, active, P.fixscale);
 }
 
 template <int MODE>
@@ -110,7 +111,7 @@ struct PairBuf {
 // the absent warps (65536 / MAXT per thread) and spend it on more pairs in flight -- bytes in flight per
 // SM, not resident warps, is what hides the HBM latency.
 // Pair indices are 32-bit (N < 2^32 particles per GPU).
-template <int K, int VAR, int MODE, int U, bool SPLIT, bool POW2, int MAXT, bool REPG>
+template <int K, int VAR, int MODE, int U, bool SPLIT, bool POW2, int MAXT, bool REPG, bool FIXED = false>
 __global__ void __launch_bounds__(MAXT, 1)
 k_vp_pass(double* __restrict__ x, double* __restrict__ v, const double* __restrict__ w,
           const double* __restrict__ dcoef, double* __restrict__ out, const PassParams P, const FinishParams F)
@@ -166,8 +167,8 @@ k_vp_pass(double* __restrict__ x, double* __restrict__ v, const double* __restri
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const bool active = (q0 + u * stride) < npairs;
-                scatter<K, VAR>(wg, P.rep_log2, rep, lane, b0[2 * u], val[2 * u], active);
-                scatter<K, VAR>(wg, P.rep_log2, rep, lane, b0[2 * u + 1], val[2 * u + 1], active);
+                scatter<K, VAR, FIXED>(wg, P.rep_log2, rep, lane, b0[2 * u], val[2 * u], active, P.fixscale);
+                scatter<K, VAR, FIXED>(wg, P.rep_log2, rep, lane, b0[2 * u + 1], val[2 * u + 1], active, P.fixscale);
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
@@ -182,8 +183,8 @@ k_vp_pass(double* __restrict__ x, double* __restrict__ v, const double* __restri
             for (int u = 0; u < U; ++u) {
                 const unsigned q = q0 + u * stride;
                 const bool active = q < npairs;
-                process<K, VAR, MODE, SPLIT, POW2, REPG>(buf[u].x.x, buf[u].v.x, buf[u].w.x, active, P, dsh, wg, rep, lane);
-                process<K, VAR, MODE, SPLIT, POW2, REPG>(buf[u].x.y, buf[u].v.y, buf[u].w.y, active, P, dsh, wg, rep, lane);
+                process<K, VAR, MODE, SPLIT, POW2, REPG, FIXED>(buf[u].x.x, buf[u].v.x, buf[u].w.x, active, P, dsh, wg, rep, lane);
+                process<K, VAR, MODE, SPLIT, POW2, REPG, FIXED>(buf[u].x.y, buf[u].v.y, buf[u].w.y, active, P, dsh, wg, rep, lane);
                 if (active && MODE != MODE_DEPOSIT) {
                     st_stream2(x + 2 * (size_t)q, buf[u].x);
                     if (MODE == MODE_PUSH_DEPOSIT) st_stream2(v + 2 * (size_t)q, buf[u].v);
@@ -235,13 +236,13 @@ k_vp_pass(double* __restrict__ x, double* __restrict__ v, const double* __restri
             if (MODE != MODE_DEPOSIT) vp = v[P.n - 1];
             wp = P.uw ? P.w0 : w[P.n - 1];
         }
-        process<K, VAR, MODE, SPLIT, POW2, REPG>(xp, vp, wp, active, P, dsh, wg, rep, lane);
+        process<K, VAR, MODE, SPLIT, POW2, REPG, FIXED>(xp, vp, wp, active, P, dsh, wg, rep, lane);
         if (active && MODE != MODE_DEPOSIT) {
             x[P.n - 1] = xp;
             if (MODE == MODE_PUSH_DEPOSIT) v[P.n - 1] = vp;
         }
     }
-    flush_grid<VAR>(grid, scratch, out, n, GHOST, P.rep_log2, nwarps, P.ncols);
+    flush_grid<VAR, FIXED>(grid, scratch, out, n, GHOST, P.rep_log2, nwarps, P.ncols);
     if (VAR != VAR_ATOMIC && F.mode != FINISH_NONE) finish_grid(F, out, gridDim.x, n, grid, scratch);
 }
 
@@ -271,14 +272,14 @@ inline PassPlan plan_pass(vm_ctx* ctx, int n, int order, int pass_mode, int depo
     return pp;
 }
 
-template <int K, int VAR, int MODE, bool SPLIT, bool POW2, int U, int MAXT, bool REPG>
+template <int K, int VAR, int MODE, bool SPLIT, bool POW2, int U, int MAXT, bool REPG, bool FIXED = false>
 void launch_pass_depth(vm_ctx* ctx, const DepositPlan& pl, double* x, double* v, const double* w,
                        const double* dcoef, double* out, const PassParams& P, const FinishParams& F)
 {
     static size_t configured[64] = {};   // per device: max dynamic smem already opted into for this instantiation
     size_t& conf = configured[ctx->device & 63];
     if (pl.smem > conf) {
-        VM_CUDA(cudaFuncSetAttribute(k_vp_pass<K, VAR, MODE, U, SPLIT, POW2, MAXT, REPG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+        VM_CUDA(cudaFuncSetAttribute(k_vp_pass<K, VAR, MODE, U, SPLIT, POW2, MAXT, REPG, FIXED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
         conf = pl.smem;
     }
     cudaLaunchConfig_t cfg{};
@@ -291,7 +292,7 @@ void launch_pass_depth(vm_ctx* ctx, const DepositPlan& pl, double* x, double* v,
     attr[0].val.programmaticStreamSerializationAllowed = ctx->no_pdl ? 0 : 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    VM_CUDA(cudaLaunchKernelEx(&cfg, k_vp_pass<K, VAR, MODE, U, SPLIT, POW2, MAXT, REPG>, x, v, w, dcoef, out, P, F));
+    VM_CUDA(cudaLaunchKernelEx(&cfg, k_vp_pass<K, VAR, MODE, U, SPLIT, POW2, MAXT, REPG, FIXED>, x, v, w, dcoef, out, P, F));
     ++ctx->launches;
 }
 
@@ -323,6 +324,13 @@ void launch_pass_inst(vm_ctx* ctx, const DepositPlan& pl, double* x, double* v, 
     const int per_sm = pl.threads * (pl.grid / ctx->sm_count);      // resident threads per SM
     const PassTier t = vm_pass_tier(MODE, VAR, per_sm, ctx->pairs);
     if (pl.threads > t.max_threads) throw vm_error(VM_ERR_UNSUPPORTED, "internal: CTA larger than the launch bound of its tier");
+    if (P.fixscale != 0.0) {      // fixed-point accumulation: lane-private layout, shallow tier (the planner sends everything else to the bank-sorted pass)
+        if constexpr (VAR == VAR_PRIV) {
+            if (P.repg) return launch_pass_depth<K, VAR, MODE, SPLIT, POW2, U0, 1024, (MODE == MODE_PUSH_DEPOSIT), true>(ctx, pl, x, v, w, dcoef, out, P, F);
+            return launch_pass_depth<K, VAR, MODE, SPLIT, POW2, U0, 1024, false, true>(ctx, pl, x, v, w, dcoef, out, P, F);
+        }
+        throw vm_error(VM_ERR_UNSUPPORTED, "internal: fixed-point deposit requested for a layout without it");
+    }
     if constexpr (VAR == VAR_PRIV) {
         if constexpr (MODE == MODE_DEPOSIT) {
             if (t.pairs == 8) return launch_pass_depth<K, VAR, MODE, SPLIT, POW2, 8, 256, false>(ctx, pl, x, v, w, dcoef, out, P, F);

@@ -112,7 +112,8 @@ __device__ __forceinline__ void bq_unpack(unsigned long long word, double& xi, u
 }
 
 // UW: all particles carry the weight P.w0 (no weight queue, no weight stream).
-template <int K, int MODE, bool SPLIT, bool POW2, bool UW, int MAXT>
+// FIXED: 64-bit fixed-point accumulation (VM_DEPOSIT_FIXED), see vm_deposit.cuh.
+template <int K, int MODE, bool SPLIT, bool POW2, bool UW, bool FIXED, int MAXT>
 __global__ void __launch_bounds__((MAXT == 1024 ? VM_BQ_MAXW * 32 : MAXT), 1)
 k_vp_pass_bq(double* __restrict__ x, double* __restrict__ v, const double* __restrict__ w,
              const double* __restrict__ dcoef, double* __restrict__ out, const PassParams P, const FinishParams F,
@@ -179,9 +180,16 @@ k_vp_pass_bq(double* __restrict__ x, double* __restrict__ v, const double* __res
         double val1[K], val2[K];
         bspline_uniform_w<K>(xi1, h1 ? wq1 : 0.0, val1);
         bspline_uniform_w<K>(xi2, h2 ? wq2 : 0.0, val2);
+        if (FIXED) {                       // round each contribution once, then integer arithmetic only
+#pragma unroll
+            for (int j = 0; j < K; ++j) {
+                val1[j] = __longlong_as_double(fix_of(val1[j], P.fixscale));
+                val2[j] = __longlong_as_double(fix_of(val2[j], P.fixscale));
+            }
+        }
         if (h2 && hi1 == hi2) {            // same rows: one read-modify-write for both (queue order: entry 1 first)
 #pragma unroll
-            for (int j = 0; j < K; ++j) val1[j] += val2[j];
+            for (int j = 0; j < K; ++j) val1[j] = acc_add<FIXED>(val1[j], val2[j]);
 #pragma unroll
             for (int j = 0; j < K; ++j) val2[j] = 0.0;
             h2 = false;
@@ -191,8 +199,8 @@ k_vp_pass_bq(double* __restrict__ x, double* __restrict__ v, const double* __res
 #pragma unroll
         for (int j = 0; j < K; ++j) {
             const double r1 = lds_f64(a1 + 8 * j), r2 = lds_f64(a2 + 8 * j);
-            sts_f64(a1 + 8 * j, r1 + val1[j]);
-            sts_f64(a2 + 8 * j, r2 + val2[j]);
+            sts_f64(a1 + 8 * j, acc_add<FIXED>(r1, val1[j]));
+            sts_f64(a2 + 8 * j, acc_add<FIXED>(r2, val2[j]));
             __syncwarp();                 // tap j of this lane and tap j + 1 of a neighbour may be the same row
         }
     };
@@ -308,7 +316,7 @@ k_vp_pass_bq(double* __restrict__ x, double* __restrict__ v, const double* __res
         push_batch(b0, xi, wp, active);
     }
     while (__any_sync(VM_FULL_MASK, head != lds_u32(s_tails + lane * 4))) pop_round();     // drain
-    flush_grid<VAR_MATCH>(grid, scratch, out, n, GHOST, 0, nwarps, P.ncols);
+    flush_grid<VAR_MATCH, FIXED>(grid, scratch, out, n, GHOST, 0, nwarps, P.ncols);
     if (F.mode != FINISH_NONE) finish_grid(F, out, gridDim.x, n, grid, scratch);
 }
 
@@ -343,14 +351,14 @@ inline bool plan_bq(vm_ctx* ctx, int n, int order, int pass_mode, bool uniform_w
     }
 }
 
-template <int K, int MODE, bool SPLIT, bool POW2, bool UW, int MAXT>
+template <int K, int MODE, bool SPLIT, bool POW2, bool UW, bool FIXED, int MAXT>
 void launch_bq_inst(vm_ctx* ctx, const BqPlan& bp, double* x, double* v, const double* w, const double* dcoef,
                     double* out, const PassParams& P, const FinishParams& F)
 {
     static size_t configured[64] = {};
     size_t& conf = configured[ctx->device & 63];
     if (bp.smem > conf) {
-        VM_CUDA(cudaFuncSetAttribute(k_vp_pass_bq<K, MODE, SPLIT, POW2, UW, MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bp.smem));
+        VM_CUDA(cudaFuncSetAttribute(k_vp_pass_bq<K, MODE, SPLIT, POW2, UW, FIXED, MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bp.smem));
         conf = bp.smem;
     }
     cudaLaunchConfig_t cfg{};
@@ -363,22 +371,30 @@ void launch_bq_inst(vm_ctx* ctx, const BqPlan& bp, double* x, double* v, const d
     attr[0].val.programmaticStreamSerializationAllowed = ctx->no_pdl ? 0 : 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    VM_CUDA(cudaLaunchKernelEx(&cfg, k_vp_pass_bq<K, MODE, SPLIT, POW2, UW, MAXT>, x, v, w, dcoef, out, P, F, bp.Q));
+    VM_CUDA(cudaLaunchKernelEx(&cfg, k_vp_pass_bq<K, MODE, SPLIT, POW2, UW, FIXED, MAXT>, x, v, w, dcoef, out, P, F, bp.Q));
     ++ctx->launches;
+}
+
+template <int K, int MODE, bool POW2, bool UW, bool FIXED>
+void launch_bq_fx(vm_ctx* ctx, const BqPlan& bp, double* x, double* v, const double* w, const double* dcoef,
+                  double* out, const PassParams& P, const FinishParams& F)
+{
+    const bool split = (MODE == MODE_PUSH_DEPOSIT) && P.kick2 != 0.0;
+    if (bp.warps <= 16) {                      // few warps: 128 registers per thread
+        if (split) launch_bq_inst<K, MODE, (MODE == MODE_PUSH_DEPOSIT), POW2, UW, FIXED, 512>(ctx, bp, x, v, w, dcoef, out, P, F);
+        else launch_bq_inst<K, MODE, false, POW2, UW, FIXED, 512>(ctx, bp, x, v, w, dcoef, out, P, F);
+    } else {
+        if (split) launch_bq_inst<K, MODE, (MODE == MODE_PUSH_DEPOSIT), POW2, UW, FIXED, 1024>(ctx, bp, x, v, w, dcoef, out, P, F);
+        else launch_bq_inst<K, MODE, false, POW2, UW, FIXED, 1024>(ctx, bp, x, v, w, dcoef, out, P, F);
+    }
 }
 
 template <int K, int MODE, bool POW2, bool UW>
 void launch_bq_uw(vm_ctx* ctx, const BqPlan& bp, double* x, double* v, const double* w, const double* dcoef,
                   double* out, const PassParams& P, const FinishParams& F)
 {
-    const bool split = (MODE == MODE_PUSH_DEPOSIT) && P.kick2 != 0.0;
-    if (bp.warps <= 16) {                      // few warps: 128 registers per thread
-        if (split) launch_bq_inst<K, MODE, (MODE == MODE_PUSH_DEPOSIT), POW2, UW, 512>(ctx, bp, x, v, w, dcoef, out, P, F);
-        else launch_bq_inst<K, MODE, false, POW2, UW, 512>(ctx, bp, x, v, w, dcoef, out, P, F);
-    } else {
-        if (split) launch_bq_inst<K, MODE, (MODE == MODE_PUSH_DEPOSIT), POW2, UW, 1024>(ctx, bp, x, v, w, dcoef, out, P, F);
-        else launch_bq_inst<K, MODE, false, POW2, UW, 1024>(ctx, bp, x, v, w, dcoef, out, P, F);
-    }
+    if (P.fixscale != 0.0) launch_bq_fx<K, MODE, POW2, UW, true>(ctx, bp, x, v, w, dcoef, out, P, F);
+    else launch_bq_fx<K, MODE, POW2, UW, false>(ctx, bp, x, v, w, dcoef, out, P, F);
 }
 
 template <int K, int MODE>

@@ -221,6 +221,7 @@ void launch_pass_bq(vm_ctx* ctx, int mode, int order, const BqPlan& bp, double* 
 
 bool want_bankq(vm_ctx* ctx, int n, int deposit_mode)
 {
+    if (deposit_mode == VM_DEPOSIT_FIXED) return n >= 8;      // (the caller prefers a shallow lane-private plan when one exists)
     if (deposit_mode != VM_DEPOSIT_DETERMINISTIC || ctx->bankq < 0) return false;
     if (ctx->ctas_per_sm > 0 || ctx->threads_per_cta > 0 || ctx->replicas > 0 || ctx->force_match) return false;   // hand-tuned round-1 variants
     return ctx->bankq > 0 ? n >= 8 : n >= VM_BQ_MIN_N;
@@ -315,11 +316,34 @@ static void pass_with_deposit(vm_field* f, vm_particles* p, int pass_mode, int d
     P.ncols = ncols;
     P.uw = vm_particles_uniform_weight(p, &P.w0) ? 1 : 0;
     BqPlan bp{};
-    const bool bq = want_bankq(ctx, n, deposit_mode) && plan_bq(ctx, n, f->order, pass_mode, P.uw != 0, &bp);
     DepositPlan pl{};
+    bool bq = false;
+    const bool fixed = deposit_mode == VM_DEPOSIT_FIXED;
+    if (fixed) {
+        // order-independent fixed-point accumulation: the shallow lane-private pass where it is the plan (small meshes),
+        // the bank-sorted pass otherwise; same bits either way (and for any launch geometry / GPU count)
+        const int S = vm_particles_fixed_scale(p);
+        P.fixscale = ldexp(1.0, S);
+        PassPlan pp{};
+        bool priv = false;
+        if (ctx->bankq <= 0) {
+            try {
+                pp = plan_pass(ctx, n, f->order, pass_mode, VM_DEPOSIT_DETERMINISTIC);
+                const PassTier t = vm_pass_tier(pass_mode, pp.pl.var, pp.pl.threads * (pp.pl.grid / ctx->sm_count), ctx->pairs);
+                priv = pp.pl.var == VAR_PRIV && t.max_threads == 1024 && t.pairs == (pass_mode == MODE_DEPOSIT ? 2 : 1);
+            } catch (const vm_error&) { priv = false; }
+        }
+        if (priv) { pl = pp.pl; P.repg = pp.repg ? 1 : 0; }
+        else {
+            bq = n >= 8 && plan_bq(ctx, n, f->order, pass_mode, P.uw != 0, &bp);
+            if (!bq) throw vm_error(VM_ERR_UNSUPPORTED, "VM_DEPOSIT_FIXED: no fixed-point deposit layout for this mesh size / tuning");
+        }
+    } else {
+        bq = want_bankq(ctx, n, deposit_mode) && plan_bq(ctx, n, f->order, pass_mode, P.uw != 0, &bp);
+    }
     if (bq) {          // bank-sorted pass: one CTA per SM, one replica grid per warp
         pl.var = VAR_MATCH; pl.rep_log2 = 0; pl.grid = ctx->sm_count; pl.threads = bp.warps * 32; pl.smem = bp.smem;
-    } else {
+    } else if (!fixed) {
         const PassPlan pp = plan_pass(ctx, n, f->order, pass_mode, deposit_mode);
         pl = pp.pl;
         P.repg = pp.repg ? 1 : 0;
@@ -348,6 +372,14 @@ static void pass_with_deposit(vm_field* f, vm_particles* p, int pass_mode, int d
             F.grows = out + (size_t)pl.grid * ncols;
         }
         if (F.mode != FINISH_NONE && xchg) vm_xchg_setup(ctx, F);   // deposit + all-gather over NVLink (+ solve) in one kernel
+        if (fixed) {
+            // the integer sums are converted to fp64 by the in-kernel finish, after the LAST addition -- across ranks that
+            // is the peer exchange (an fp64 NCCL all-reduce of converted partial sums would depend on the rank count)
+            if (F.mode == FINISH_NONE) throw vm_error(VM_ERR_UNSUPPORTED, "VM_DEPOSIT_FIXED needs the fused finish (n_basis <= 1024, tuning no_fuse = 0)");
+            if (ctx->nranks > 1 && want_solve && !F.xchg) throw vm_error(VM_ERR_UNSUPPORTED, "VM_DEPOSIT_FIXED across ranks needs the peer-memory exchange (vm_ctx_peer_connect)");
+            F.fixed = 1;
+            F.inv_scale = 1.0 / P.fixscale;
+        }
     }
     // the dominant kernel of its caller: the fused pass inside vm_vp_run, the deposit pass elsewhere
     const bool prof = (pass_mode == MODE_PUSH_DEPOSIT) || (pass_mode == MODE_DEPOSIT && prof_deposit);
@@ -391,7 +423,7 @@ int vm_pass_plan_query(int sm_count, size_t smem_optin_bytes, int n_basis, int o
         VM_REQUIRE(n_basis >= 1 && n_basis <= VM_MAX_NBASIS, "vm_pass_plan_query: n_basis out of range");
         VM_REQUIRE(order >= VM_MIN_ORDER && order <= VM_MAX_ORDER, "vm_pass_plan_query: spline order must be in 2..6");
         VM_REQUIRE(pass >= 0 && pass <= 2, "vm_pass_plan_query: pass must be 0 (deposit), 1 (fused step) or 2 (drift + deposit)");
-        VM_REQUIRE(deposit_mode == VM_DEPOSIT_DETERMINISTIC || deposit_mode == VM_DEPOSIT_ATOMIC, "vm_pass_plan_query: unknown mode");
+        VM_REQUIRE(deposit_mode == VM_DEPOSIT_DETERMINISTIC || deposit_mode == VM_DEPOSIT_ATOMIC, "vm_pass_plan_query: unknown mode (the fixed-point mode picks between the plans of mode 0 at run time)");
         vm_ctx dev;                      // host-side description only: no CUDA call is made
         dev.sm_count = sm_count;
         dev.smem_optin = smem_optin_bytes;
@@ -428,7 +460,7 @@ int vm_deposit(vm_field* f, vm_particles* p, int mode)
 {
     VM_API_BEGIN(f ? f->ctx : nullptr)
     check_pair(f, p, "vm_deposit");
-    VM_REQUIRE(mode == VM_DEPOSIT_DETERMINISTIC || mode == VM_DEPOSIT_ATOMIC, "vm_deposit: unknown mode");
+    VM_REQUIRE(mode == VM_DEPOSIT_DETERMINISTIC || mode == VM_DEPOSIT_ATOMIC || mode == VM_DEPOSIT_FIXED, "vm_deposit: unknown mode");
     PassParams P{};
     pass_with_deposit(f, p, MODE_DEPOSIT, mode, P, false, true);
     VM_API_END
@@ -526,7 +558,8 @@ int vm_vp_run(vm_field* f, vm_particles* p, double dt, int nsteps, int diag_ever
     const bool split = (flags & VM_RUN_SPLIT_KICK) != 0;
     const bool frozen = (flags & VM_RUN_FROZEN_FIELD) != 0;
     const bool unfused = (flags & VM_RUN_UNFUSED) != 0;
-    const int dmode = (flags & VM_RUN_ATOMIC_DEPOSIT) ? VM_DEPOSIT_ATOMIC : VM_DEPOSIT_DETERMINISTIC;
+    const int dmode = (flags & VM_RUN_ATOMIC_DEPOSIT) ? VM_DEPOSIT_ATOMIC
+                      : ((flags & VM_RUN_FIXED_DEPOSIT) ? VM_DEPOSIT_FIXED : VM_DEPOSIT_DETERMINISTIC);
     const double k1 = split ? 0.5 * kick_full : kick_full, k2 = split ? 0.5 * kick_full : 0.0;
     const double hd = 0.5 * dte;
     const int nrows = diag_every > 0 ? nsteps / diag_every + 1 : 0;
