@@ -71,7 +71,7 @@ inline size_t vm_gather_table_doubles(int n, int order, bool repg) { return (siz
 // SPLIT: two half kicks (new-API Strang) instead of one.  The fused mode always applies the two
 // separately rounded half drifts of consecutive Strang steps (drift1 then drift2).
 // Phase A of a particle: everything up to the deposit weights (reads the read-only dcoef table only).
-template <int K, int MODE, bool SPLIT, bool POW2, bool REPG>
+template <int K, int MODE, bool SPLIT, bool POW2, bool REPG, bool FIXED = false>
 __device__ __forceinline__ void prepare(double& xp, double& vp, double wp, const PassParams& P,
                                         const double* __restrict__ dsh, int& b0, double (&val)[K])
 {
@@ -87,6 +87,11 @@ __device__ __forceinline__ void prepare(double& xp, double& vp, double wp, const
     if (MODE != MODE_DEPOSIT) xp = __dadd_rn(xp, __dmul_rn(P.drift1, vp));
     if (MODE == MODE_PUSH_DEPOSIT) xp = __dadd_rn(xp, __dmul_rn(P.drift2, vp));
     cell_of<CONV, POW2>(P.map, xp, b0, xi);
+    if (FIXED) {
+        // the fixed-point deposit must round the SAME per-particle numbers in every layout: the bank-sorted pass
+        // carries xi as the 52-bit mantissa of xi + 1 (vm_pass_bq.cuh: bq_pack), so that is the canonical xi
+        xi = (fmin(xi, 0x1.fffffffffffffp-1) + 1.0) - 1.0;
+    }
     bspline_uniform_w<K>(xi, wp, val);                 // inactive lanes carry wp == 0
 }
 
@@ -96,7 +101,7 @@ __device__ __forceinline__ void process(double& xp, double& vp, double wp, bool 
 {
     int b0;
     double val[K];
-    prepare<K, MODE, SPLIT, POW2, REPG>(xp, vp, wp, P, dsh, b0, val);
+    prepare<K, MODE, SPLIT, POW2, REPG, FIXED>(xp, vp, wp, P, dsh, b0, val);
     scatter<K, VAR, FIXED>(wg, P.rep_log2, rep, lane, b0, val, active, P.fixscale);
 }
 
@@ -161,8 +166,8 @@ k_vp_pass(double* __restrict__ x, double* __restrict__ v, const double* __restri
             double val[2 * U][K];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                prepare<K, MODE, SPLIT, POW2, REPG>(buf[u].x.x, buf[u].v.x, buf[u].w.x, P, dsh, b0[2 * u], val[2 * u]);
-                prepare<K, MODE, SPLIT, POW2, REPG>(buf[u].x.y, buf[u].v.y, buf[u].w.y, P, dsh, b0[2 * u + 1], val[2 * u + 1]);
+                prepare<K, MODE, SPLIT, POW2, REPG, FIXED>(buf[u].x.x, buf[u].v.x, buf[u].w.x, P, dsh, b0[2 * u], val[2 * u]);
+                prepare<K, MODE, SPLIT, POW2, REPG, FIXED>(buf[u].x.y, buf[u].v.y, buf[u].w.y, P, dsh, b0[2 * u + 1], val[2 * u + 1]);
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
