@@ -202,7 +202,7 @@ VM_DECL_PASS_BQ(2) VM_DECL_PASS_BQ(3) VM_DECL_PASS_BQ(4) VM_DECL_PASS_BQ(5) VM_D
 
 // Meshes from this size on run the bank-sorted pass (vm_pass_bq.cuh); below it lane-private replicas fit with enough
 // warps.  Tuning key "bankq": 0 = this rule (the first size without a lane-private plan), 1 = always (n >= 8), -1 = never (A/B: the round-1 variants).
-#define VM_BQ_MIN_N 129
+#define VM_BQ_MIN_N 88
 
 namespace {
 

@@ -80,8 +80,12 @@ __device__ __forceinline__ void vdeposit_one(double vp, double wp, bool active, 
     scatter<K, VAR>(wg, rep_log2, rep, lane, c, val, active);
 }
 
-template <int K, int VAR>
-__global__ void __launch_bounds__(1024, 1)
+// U = pairs of particles per thread and half-iteration, MAXT = launch bound (as k_vp_pass): the lane-private replica
+// grids of the default 41-knot basis leave room for 20 warps, which get 96 registers and, per half-iteration, the
+// cell/weight computation of the whole batch ahead of its read-modify-writes (ncu, round 2: the 2-pair / 64-register
+// form ran at 62 % issue-active, 64 % of the shared-memory wavefront rate and 31 % occupancy -- latency-bound).
+template <int K, int VAR, int U, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1)
 k_v_deposit(const double* __restrict__ v, const double* __restrict__ w, long np, VCell m,
             const double* __restrict__ cellpoly, int npar, int rep_log2, double* __restrict__ out,
             const FinishParams F, int uw, double w0)
@@ -97,9 +101,8 @@ k_v_deposit(const double* __restrict__ v, const double* __restrict__ w, long np,
     double* wg = (VAR == VAR_ATOMIC) ? grid : grid + warp * gsz;
     const int rep = ((VAR == VAR_ATOMIC) ? warp : lane) & ((1 << rep_log2) - 1);
 
-    // 16 B/particle, issue-bound pass: same loop shape as the x-space deposit-only pass (two pairs in
-    // flight per thread, unrolled twice over two register buffer sets, 32-bit pair indices)
-    constexpr int U = 2;
+    // 8-16 B/particle pass: same loop shape as the x-space deposit-only pass (unrolled twice over two register
+    // buffer sets, 32-bit pair indices)
     const unsigned npairs = (unsigned)(np >> 1);
     const unsigned stride = gridDim.x * blockDim.x;
     const unsigned gtid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -118,11 +121,24 @@ k_v_deposit(const double* __restrict__ v, const double* __restrict__ w, long np,
         }
     };
     auto work = [&](double2 (&bv)[U], double2 (&bw)[U], unsigned q0) {
+        if constexpr (VAR == VAR_PRIV && MAXT < 1024) {
+            int c[2 * U];
+            double val[2 * U][K];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const bool active = (q0 + u * stride) < npairs;
-            vdeposit_one<K, VAR>(bv[u].x, bw[u].x, active, m, cellpoly, wg, npar, rep_log2, rep, lane);
-            vdeposit_one<K, VAR>(bv[u].y, bw[u].y, active, m, cellpoly, wg, npar, rep_log2, rep, lane);
+            for (int u = 0; u < U; ++u) {      // (inactive or out-of-domain particles come back with zero weights)
+                const bool active = (q0 + u * stride) < npairs;
+                vdeposit_prepare<K, true>(bv[u].x, bw[u].x, active, m, cellpoly, c[2 * u], val[2 * u]);
+                vdeposit_prepare<K, true>(bv[u].y, bw[u].y, active, m, cellpoly, c[2 * u + 1], val[2 * u + 1]);
+            }
+#pragma unroll
+            for (int u = 0; u < 2 * U; ++u) scatter<K, VAR>(wg, rep_log2, rep, lane, c[u], val[u], true);
+        } else {
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const bool active = (q0 + u * stride) < npairs;
+                vdeposit_one<K, VAR>(bv[u].x, bw[u].x, active, m, cellpoly, wg, npar, rep_log2, rep, lane);
+                vdeposit_one<K, VAR>(bv[u].y, bw[u].y, active, m, cellpoly, wg, npar, rep_log2, rep, lane);
+            }
         }
     };
 #pragma unroll
@@ -608,20 +624,32 @@ void geometry(vm_ctx* ctx, int* grid, int* threads)
     if (*threads > 512) *threads = 512;
 }
 
-template <int K, int VAR>
-void launch_vdep_inst(vm_vspline* s, const DepositPlan& pl, const double* v, const double* w, long np, double* out,
+template <int K, int VAR, int U, int MAXT>
+void launch_vdep_tier(vm_vspline* s, const DepositPlan& pl, const double* v, const double* w, long np, double* out,
                       const FinishParams& F)
 {
     vm_ctx* ctx = s->ctx;
     static size_t configured[64] = {};
     size_t& conf = configured[ctx->device & 63];
     if (pl.smem > conf) {
-        VM_CUDA(cudaFuncSetAttribute(k_v_deposit<K, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+        VM_CUDA(cudaFuncSetAttribute(k_v_deposit<K, VAR, U, MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
         conf = pl.smem;
     }
-    k_v_deposit<K, VAR><<<pl.grid, pl.threads, pl.smem, ctx->stream>>>(v, w, np, vcell(s), s->cellpoly, s->npar,
-                                                                      pl.rep_log2, out, F, s->uw, s->w0);
+    k_v_deposit<K, VAR, U, MAXT><<<pl.grid, pl.threads, pl.smem, ctx->stream>>>(v, w, np, vcell(s), s->cellpoly, s->npar,
+                                                                               pl.rep_log2, out, F, s->uw, s->w0);
     VM_LAUNCHED(ctx);
+}
+
+template <int K, int VAR>
+void launch_vdep_inst(vm_vspline* s, const DepositPlan& pl, const double* v, const double* w, long np, double* out,
+                      const FinishParams& F)
+{
+    if constexpr (VAR == VAR_PRIV) {          // few lane-private warps: deeper software pipeline (pairs == 1: A/B switch back)
+        const int per_sm = pl.threads * (pl.grid / s->ctx->sm_count);
+        if (per_sm <= 320 && s->ctx->pairs != 1) return launch_vdep_tier<K, VAR, 4, 320>(s, pl, v, w, np, out, F);
+        if (per_sm <= 640 && s->ctx->pairs != 1) return launch_vdep_tier<K, VAR, 2, 640>(s, pl, v, w, np, out, F);
+    }
+    launch_vdep_tier<K, VAR, 2, 1024>(s, pl, v, w, np, out, F);
 }
 
 template <int K>
