@@ -36,7 +36,7 @@
 #define VM_BQ_CAP (1 << VM_BQ_CAP_LOG2)
 #define VM_BQ_QWORDS (32 * VM_BQ_CAP)          // 64-bit words per warp queue array
 #define VM_BQ_TAILWORDS 16                     // 32 x u32 queue tails per warp (as 64-bit words)
-#define VM_BQ_SINKWORDS 40                     // per-warp sink row (32 + K - 1 doubles, padded): zeros of idle lanes land here
+#define VM_BQ_SINKWORDS 56                     // per-warp sink row (32 + K - 1 doubles + 15 of alignment slack): zeros of idle lanes land here
 // The pass is instruction-issue bound (ncu: 76 % issue-active, 298 warp instructions per warp of particles in its first
 // version), so the cell lookup uses the 2-instruction FRND/F2I form (quarter-rate conversion pipe, idle here) rather
 // than the 5-instruction magic-number floor of the HBM-bound lane-private pass.
@@ -135,7 +135,7 @@ k_vp_pass_bq(double* __restrict__ x, double* __restrict__ v, const double* __res
     for (int i = threadIdx.x; i < gtotal; i += blockDim.x) grid[i] = 0.0;
     tails[lane] = 0u;
     sink[lane] = 0.0;
-    if (lane < K - 1) sink[32 + lane] = 0.0;
+    if (lane < VM_BQ_SINKWORDS - 32) sink[32 + lane] = 0.0;
     asm volatile("griddepcontrol.wait;" ::: "memory");
     if (MODE == MODE_PUSH_DEPOSIT) {
         const int ext = K - 2 > 0 ? K - 2 : 0, copies = 1 << Q.gshift;
@@ -149,7 +149,10 @@ k_vp_pass_bq(double* __restrict__ x, double* __restrict__ v, const double* __res
     const int gshift = Q.gshift, stride_b = 8 << gshift;
     const unsigned s_tab = smem_u32(dsh) + (lane & ((1 << gshift) - 1)) * 8;
     const unsigned s_rows = smem_u32(grid + warp * gsz) + lane * 8;      // row (hi << 5 | lane) of my warp's grid at s_rows + hi * 256
-    const unsigned s_sink = smem_u32(sink) + lane * 8;
+    // the sink slot of lane l must sit in the SAME bank pair as the rows lane l owns (rows_base + l + j): an idle lane's
+    // access then never conflicts with an active lane's (ncu, first version: 37 % of all shared wavefronts of the pass were
+    // such 2-way conflicts) -- shift the sink row by the bank-pair offset between the two regions
+    const unsigned s_sink = smem_u32(sink) + lane * 8 + ((((s_rows - lane * 8) - smem_u32(sink)) >> 3) & 15u) * 8;
     const unsigned s_tails = smem_u32(tails);
     const unsigned s_q = smem_u32(qbase);                                // entry e of class c at s_q + (e & (CAP - 1)) * 256 + c * 8
     constexpr unsigned WOFF = VM_BQ_QWORDS * 8;                          // byte offset of the weight queue
