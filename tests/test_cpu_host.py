@@ -160,11 +160,12 @@ def test_pass_plans_of_the_benchmarked_meshes(vm):
     assert (p.variant, p.grid, p.threads, p.pairs, p.gather_copies) == (0, 148, 768, 1, 16)
     p = L.pass_plan(64, 4, 1)
     assert (p.variant, p.grid, p.threads, p.pairs, p.max_threads, p.gather_copies) == (0, 148, 384, 4, 448, 16)
-    p = L.pass_plan(128, 4, 1)
-    assert (p.variant, p.grid, p.threads, p.pairs, p.max_threads, p.gather_copies) == (0, 148, 192, 8, 192, 16)
-    p = L.pass_plan(128, 4, 0)
-    assert (p.variant, p.threads, p.pairs, p.max_threads) == (0, 192, 8, 256)
-    assert L.pass_plan(256, 4, 1).variant == 4 and L.pass_plan(1024, 4, 1).variant == 4      # bank-sorted queues
+    p = L.pass_plan(80, 4, 1)                             # the last mesh with a lane-private plan (VM_BQ_MIN_N = 88)
+    assert (p.variant, p.grid, p.threads, p.pairs, p.max_threads, p.gather_copies) == (0, 148, 320, 4, 448, 16)
+    p = L.pass_plan(128, 4, 1)                            # bank-sorted queues from 88 cells on (profiles/r02_bankq_threshold.jsonl)
+    assert (p.variant, p.grid, p.threads, p.pairs, p.max_threads, p.gather_copies) == (4, 148, 1024, 1, 1024, 16)
+    assert L.pass_plan(128, 4, 0).variant == 4 and L.pass_plan(88, 4, 1).variant == 4
+    assert L.pass_plan(256, 4, 1).variant == 4 and L.pass_plan(1024, 4, 1).variant == 4
     assert L.pass_plan(16, 4, 0, 1).variant == 2          # VM_DEPOSIT_ATOMIC: the warp-aggregated A/B variant
     for bad in ((0, 4, 1), (16, 7, 1), (16, 4, 3), (5000, 4, 1)):
         with pytest.raises(vm.VMError):
