@@ -289,6 +289,8 @@ int vm_ctx_set_tuning(vm_ctx* ctx, const char* key, int value)
         ctx->priv_min_warps = value;
     }
     else if (k == "bankq") { VM_REQUIRE(value >= -1 && value <= 1, "bankq must be -1, 0 or 1"); ctx->bankq = value; }
+    else if (k == "af") { VM_REQUIRE(value >= -1 && value <= 1, "af must be -1, 0 or 1"); ctx->af = value; }
+    else if (k == "af_ctas") { VM_REQUIRE(value >= 0 && value <= 4 && value != 3, "af_ctas must be 0, 1, 2 or 4"); ctx->af_ctas = value; }
     else if (k == "no_repg") ctx->no_repg = value;   // 1: single (bank-conflicting) gather table in the fused pass (A/B)
     else if (k == "profile") ctx->profile = value;
     else if (k == "force_match") ctx->force_match = value;   // 1: MATCH.ANY grouping instead of xor rounds (A/B)
@@ -577,6 +579,7 @@ int vm_particles_fixed_scale(vm_particles* p)
         if (S < -1000) S = -1000;
     }
     p->fix_S = S;
+    p->fix_ok = (wmax == 0.0) || (wmax > 0.0 && wmax < 1e300);     // (NaN / infinite weights: the fp64 layouts propagate them)
     p->fix_dirty = false;
     p->fix_nranks = ctx->nranks;
     return S;

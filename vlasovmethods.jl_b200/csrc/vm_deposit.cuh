@@ -8,7 +8,7 @@
 #pragma once
 #include "vm_internal.cuh"
 
-enum { VAR_PRIV = 0, VAR_MATCH = 1, VAR_ATOMIC = 2, VAR_XOR = 3 };
+enum { VAR_PRIV = 0, VAR_MATCH = 1, VAR_ATOMIC = 2, VAR_XOR = 3, VAR_AF = 5 };   // (4 is the bank-sorted pass in vm_pass_plan.variant)
 
 // ------------------------------------------------ order-independent sums -----
 // VM_DEPOSIT_FIXED: every contribution w * B_j(xi) is rounded ONCE to a 64-bit fixed-point integer (scale 2^S, S
@@ -40,7 +40,35 @@ template <int K, int VAR, bool FIXED = false>
 __device__ __forceinline__ void scatter(double* __restrict__ wg, int rep_log2, int rep, int lane,
                                         int b0, const double (&val)[K], bool active, double fixscale = 0.0)
 {
-    static_assert(!FIXED || VAR == VAR_PRIV, "fixed-point accumulation exists in the lane-private and bank-sorted layouts");
+    static_assert(!FIXED || VAR == VAR_PRIV || VAR == VAR_AF, "fixed-point accumulation exists in the lane-private, bank-sorted and limb-atomic layouts");
+    static_assert(FIXED || VAR != VAR_AF, "the limb-atomic layout accumulates fixed-point integers");
+    if (VAR == VAR_AF) {
+        // ONE grid per CTA for all warps, each row a 64-bit fixed-point integer stored as two 32-bit limbs in two
+        // arrays (lo[rows] then hi[rows]: consecutive rows in consecutive banks).  64-bit and fp64 shared-memory
+        // atomics are CAS loops on sm_100a (ATOMS.CAST.SPIN), 32-bit integer adds are native (ATOMS.ADD): add the low
+        // limb with a returning atomic, derive the carry from the returned value, add high limb + carry with a second
+        // one.  Every limb update is atomic and every wrap of a low limb is carried exactly once by the thread that
+        // caused it, so after all adds (hi:lo) is the exact sum mod 2^64 in ANY order; collisions and bank conflicts
+        // are serialised by the hardware, no replicas, no sorting, no warp-collective step.  Measured (tools/microbench/
+        // atoms.cu): 21 clocks per warp of particles for the 8 atomics of a cubic deposit on random rows, any mesh size
+        // (the un-handled LDS/DADD/STS form on one replica: 36-40).  wg = lo words, rep = word offset of the hi array.
+        if (active) {
+            unsigned* lo = (unsigned*)wg + b0;
+#pragma unroll
+            for (int j = 0; j < K; ++j) {
+                // fix_of by limbs: the low word of the magic constant is zero, so the low limb is the low word of the
+                // fma itself and only the high word needs the subtraction
+                const double r = fma(val[j], fixscale, VM_FIX_MAGIC);
+                const unsigned xl = (unsigned)__double2loint(r);
+                const unsigned xh = (unsigned)__double2hiint(r) - 0x43380000u;
+                const unsigned old = atomicAdd(lo + j, xl);
+                unsigned t, h;
+                asm("add.cc.u32 %0, %2, %3;\n\taddc.u32 %1, %4, 0;" : "=r"(t), "=r"(h) : "r"(old), "r"(xl), "r"(xh));
+                atomicAdd(lo + rep + j, h);
+            }
+        }
+        return;
+    }
     if (VAR == VAR_PRIV) {
         // one private column per lane: no collisions, no branches, immediate-offset LDS/DADD/STS
         if (FIXED) {
@@ -173,6 +201,21 @@ __device__ __forceinline__ void flush_grid(double* __restrict__ grid, double* __
         }
         __syncthreads();
     }
+}
+
+// Limb-atomic layout (VAR_AF): join the limbs of every row, fold the ghost rows and emit the CTA's partial row -- as the
+// 64-bit integer itself when the fused finish continues in integers (as_bits), converted to fp64 otherwise.
+__device__ __forceinline__ void flush_limbs(const unsigned* __restrict__ lo, double* __restrict__ out, int n, int ghost,
+                                            int ncols, bool as_bits, double inv_scale)
+{
+    const unsigned* hi = lo + n + ghost;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        long long s = (long long)(((unsigned long long)hi[i] << 32) | lo[i]);
+        if (i < ghost) s += (long long)(((unsigned long long)hi[n + i] << 32) | lo[n + i]);
+        out[(size_t)blockIdx.x * ncols + i] = as_bits ? __longlong_as_double(s) : (double)s * inv_scale;
+    }
+    __syncthreads();
 }
 
 // ------------------------------------------------ fused cross-CTA finish ----

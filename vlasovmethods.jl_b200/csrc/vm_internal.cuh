@@ -57,6 +57,7 @@ struct vm_ctx {
     // tuning (0 = auto)
     int ctas_per_sm = 0, threads_per_cta = 0, replicas = 0, profile = 0, no_fuse = 0, no_pdl = 0, force_match = 0, no_uniform_w = 0;
     int bankq = 0;      // bank-sorted large-mesh pass: 0 = auto (n >= 256), 1 = always, -1 = never
+    int af = 0, af_ctas = 0;   // limb-atomic fixed-point pass: 0 = auto (from VM_AF_MIN_N cells), 1 = always, -1 = never; CTAs per SM (0 = auto)
     int pairs = 0, priv_min_warps = 0, no_repg = 0;   // pairs in flight per thread / fewest warps the lane-private deposit accepts
     // per-launch event brackets of the dominant kernel (profile == 1)
     std::vector<cudaEvent_t> prof_events;   // pairs: [2i] start, [2i+1] stop
@@ -96,6 +97,7 @@ struct vm_particles {
     // fixed-point scale of VM_DEPOSIT_FIXED (vm_particles_fixed_scale): valid until the weights or the communicator change
     bool fix_dirty = true;
     int fix_S = 0;
+    bool fix_ok = false;        // the weights admit a fixed-point scale (finite, max |w| < 1e300)
     int fix_nranks = 0;
 };
 

@@ -127,12 +127,13 @@ k_vp_pass(double* __restrict__ x, double* __restrict__ v, const double* __restri
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     double* dsh = smem;
     double* grid = smem + (MODE == MODE_PUSH_DEPOSIT ? (n + K) * (REPG ? VM_GATHER_COPIES : 1) : 0);
-    const int gsz = (n + GHOST) << P.rep_log2;
-    const int gtotal = (VAR == VAR_ATOMIC) ? gsz : gsz * nwarps;
-    double* scratch = grid + gtotal;
+    const int gsz = (VAR == VAR_AF) ? (n + GHOST) : ((n + GHOST) << P.rep_log2);     // VAR_AF: (n + GHOST) lo words + as many hi words
+    const int gtotal = (VAR == VAR_ATOMIC || VAR == VAR_AF) ? gsz : gsz * nwarps;
+    // (VAR_AF: the finish needs 3n + 1 doubles of work area where the limb arrays were, see vm_af_core_doubles)
+    double* scratch = grid + ((VAR == VAR_AF && 3 * n + 2 > gtotal) ? 3 * n + 2 : gtotal);
     for (int i = threadIdx.x; i < gtotal; i += blockDim.x) grid[i] = 0.0;
-    double* wg = (VAR == VAR_ATOMIC) ? grid : grid + warp * gsz;
-    const int rep = ((VAR == VAR_ATOMIC) ? warp : lane) & ((1 << P.rep_log2) - 1);
+    double* wg = (VAR == VAR_ATOMIC || VAR == VAR_AF) ? grid : grid + warp * gsz;
+    const int rep = (VAR == VAR_AF) ? gsz : (((VAR == VAR_ATOMIC) ? warp : lane) & ((1 << P.rep_log2) - 1));
 
     const unsigned npairs = (unsigned)(P.n >> 1);
     const unsigned stride = gridDim.x * blockDim.x;
@@ -247,7 +248,8 @@ k_vp_pass(double* __restrict__ x, double* __restrict__ v, const double* __restri
             if (MODE == MODE_PUSH_DEPOSIT) v[P.n - 1] = vp;
         }
     }
-    flush_grid<VAR, FIXED>(grid, scratch, out, n, GHOST, P.rep_log2, nwarps, P.ncols);
+    if (VAR == VAR_AF) flush_limbs((const unsigned*)grid, out, n, GHOST, P.ncols, F.mode != FINISH_NONE && F.fixed, F.inv_scale);
+    else flush_grid<VAR, FIXED>(grid, scratch, out, n, GHOST, P.rep_log2, nwarps, P.ncols);
     if (VAR != VAR_ATOMIC && F.mode != FINISH_NONE) finish_grid(F, out, gridDim.x, n, grid, scratch);
 }
 
@@ -275,6 +277,29 @@ inline PassPlan plan_pass(vm_ctx* ctx, int n, int order, int pass_mode, int depo
         pp.pl = plan_deposit(ctx, n, order - 1, pass_mode == MODE_PUSH_DEPOSIT ? (int)vm_gather_table_doubles(n, order, false) : 0,
                              deposit_mode, pmw);
     return pp;
+}
+
+// Limb-atomic pass (VAR_AF): one grid of (n + K - 1) two-limb rows per CTA -- shared memory is no constraint, so the
+// CTA shape is that of the small-mesh pass (1024 threads per SM, two CTAs when two gather tables fit) and the gather
+// table is stored 16-fold whenever it fits.  ctas_req / threads_req: tuning keys af_ctas (0 = auto).
+inline size_t vm_af_core_doubles(int n, int order) { return (size_t)((3 * n + 2 > n + order - 1) ? 3 * n + 2 : n + order - 1); }
+inline bool plan_af(vm_ctx* ctx, int n, int order, int pass_mode, PassPlan* out)
+{
+    const size_t sm_total = 227 * 1024;
+    for (int rg = 1; rg >= 0; --rg) {
+        if (rg && (pass_mode != MODE_PUSH_DEPOSIT || n <= 16 || ctx->no_repg)) continue;
+        for (int ctas = (ctx->af_ctas > 0 ? ctx->af_ctas : 2); ctas >= 1; --ctas) {
+            const int threads = 1024 / ctas;
+            const size_t table = pass_mode == MODE_PUSH_DEPOSIT ? vm_gather_table_doubles(n, order, rg != 0) : 0;
+            const size_t smem = (table + vm_af_core_doubles(n, order) + (size_t)threads) * sizeof(double);
+            if (smem <= ctx->smem_optin && (size_t)ctas * (smem + 1024) <= sm_total && threads >= 128) {
+                out->pl = DepositPlan{VAR_AF, 0, ctx->sm_count * ctas, threads, smem};
+                out->repg = rg != 0;
+                return true;
+            }
+        }
+    }
+    return false;
 }
 
 template <int K, int VAR, int MODE, bool SPLIT, bool POW2, int U, int MAXT, bool REPG, bool FIXED = false>
@@ -320,7 +345,7 @@ inline PassTier vm_pass_tier(int mode, int var, int per_sm, int pairs_req)
     return base;
 }
 
-// P.repg (lane-private fused pass on meshes with more than 16 cells): replicated gather table.
+// P.repg (lane-private and limb-atomic fused passes on meshes with more than 16 cells): replicated gather table.
 template <int K, int VAR, int MODE, bool SPLIT, bool POW2>
 void launch_pass_inst(vm_ctx* ctx, const DepositPlan& pl, double* x, double* v, const double* w,
                       const double* dcoef, double* out, const PassParams& P, const FinishParams& F)
@@ -329,28 +354,34 @@ void launch_pass_inst(vm_ctx* ctx, const DepositPlan& pl, double* x, double* v, 
     const int per_sm = pl.threads * (pl.grid / ctx->sm_count);      // resident threads per SM
     const PassTier t = vm_pass_tier(MODE, VAR, per_sm, ctx->pairs);
     if (pl.threads > t.max_threads) throw vm_error(VM_ERR_UNSUPPORTED, "internal: CTA larger than the launch bound of its tier");
-    if (P.fixscale != 0.0) {      // fixed-point accumulation: lane-private layout, shallow tier (the planner sends everything else to the bank-sorted pass)
+    if constexpr (VAR == VAR_AF) {     // limb atomics: always fixed-point, shallow tier
+        if (P.fixscale == 0.0) throw vm_error(VM_ERR_UNSUPPORTED, "internal: the limb-atomic deposit needs a fixed-point scale");
+        if (P.repg) return launch_pass_depth<K, VAR, MODE, SPLIT, POW2, U0, 1024, (MODE == MODE_PUSH_DEPOSIT), true>(ctx, pl, x, v, w, dcoef, out, P, F);
+        return launch_pass_depth<K, VAR, MODE, SPLIT, POW2, U0, 1024, false, true>(ctx, pl, x, v, w, dcoef, out, P, F);
+    } else {
+        if (P.fixscale != 0.0) {      // fixed-point accumulation: lane-private layout, shallow tier (the planner sends everything else to the limb-atomic or bank-sorted pass)
+            if constexpr (VAR == VAR_PRIV) {
+                if (P.repg) return launch_pass_depth<K, VAR, MODE, SPLIT, POW2, U0, 1024, (MODE == MODE_PUSH_DEPOSIT), true>(ctx, pl, x, v, w, dcoef, out, P, F);
+                return launch_pass_depth<K, VAR, MODE, SPLIT, POW2, U0, 1024, false, true>(ctx, pl, x, v, w, dcoef, out, P, F);
+            }
+            throw vm_error(VM_ERR_UNSUPPORTED, "internal: fixed-point deposit requested for a layout without it");
+        }
         if constexpr (VAR == VAR_PRIV) {
-            if (P.repg) return launch_pass_depth<K, VAR, MODE, SPLIT, POW2, U0, 1024, (MODE == MODE_PUSH_DEPOSIT), true>(ctx, pl, x, v, w, dcoef, out, P, F);
-            return launch_pass_depth<K, VAR, MODE, SPLIT, POW2, U0, 1024, false, true>(ctx, pl, x, v, w, dcoef, out, P, F);
+            if constexpr (MODE == MODE_DEPOSIT) {
+                if (t.pairs == 8) return launch_pass_depth<K, VAR, MODE, SPLIT, POW2, 8, 256, false>(ctx, pl, x, v, w, dcoef, out, P, F);
+                if (t.pairs == 4) return launch_pass_depth<K, VAR, MODE, SPLIT, POW2, 4, 512, false>(ctx, pl, x, v, w, dcoef, out, P, F);
+            } else if constexpr (MODE == MODE_DRIFT_DEPOSIT) {
+                if (t.pairs == 8) return launch_pass_depth<K, VAR, MODE, SPLIT, POW2, 8, 192, false>(ctx, pl, x, v, w, dcoef, out, P, F);
+                if (t.pairs == 4) return launch_pass_depth<K, VAR, MODE, SPLIT, POW2, 4, 448, false>(ctx, pl, x, v, w, dcoef, out, P, F);
+            } else if (P.repg) {
+                if (t.pairs == 8) return launch_pass_depth<K, VAR, MODE, SPLIT, POW2, 8, 192, true>(ctx, pl, x, v, w, dcoef, out, P, F);
+                if (t.pairs == 4) return launch_pass_depth<K, VAR, MODE, SPLIT, POW2, 4, 448, true>(ctx, pl, x, v, w, dcoef, out, P, F);
+                return launch_pass_depth<K, VAR, MODE, SPLIT, POW2, 1, 1024, true>(ctx, pl, x, v, w, dcoef, out, P, F);
+            }
         }
-        throw vm_error(VM_ERR_UNSUPPORTED, "internal: fixed-point deposit requested for a layout without it");
+        if (P.repg) throw vm_error(VM_ERR_UNSUPPORTED, "internal: replicated gather table requested for a deposit variant without it");
+        launch_pass_depth<K, VAR, MODE, SPLIT, POW2, U0, 1024, false>(ctx, pl, x, v, w, dcoef, out, P, F);
     }
-    if constexpr (VAR == VAR_PRIV) {
-        if constexpr (MODE == MODE_DEPOSIT) {
-            if (t.pairs == 8) return launch_pass_depth<K, VAR, MODE, SPLIT, POW2, 8, 256, false>(ctx, pl, x, v, w, dcoef, out, P, F);
-            if (t.pairs == 4) return launch_pass_depth<K, VAR, MODE, SPLIT, POW2, 4, 512, false>(ctx, pl, x, v, w, dcoef, out, P, F);
-        } else if constexpr (MODE == MODE_DRIFT_DEPOSIT) {
-            if (t.pairs == 8) return launch_pass_depth<K, VAR, MODE, SPLIT, POW2, 8, 192, false>(ctx, pl, x, v, w, dcoef, out, P, F);
-            if (t.pairs == 4) return launch_pass_depth<K, VAR, MODE, SPLIT, POW2, 4, 448, false>(ctx, pl, x, v, w, dcoef, out, P, F);
-        } else if (P.repg) {
-            if (t.pairs == 8) return launch_pass_depth<K, VAR, MODE, SPLIT, POW2, 8, 192, true>(ctx, pl, x, v, w, dcoef, out, P, F);
-            if (t.pairs == 4) return launch_pass_depth<K, VAR, MODE, SPLIT, POW2, 4, 448, true>(ctx, pl, x, v, w, dcoef, out, P, F);
-            return launch_pass_depth<K, VAR, MODE, SPLIT, POW2, 1, 1024, true>(ctx, pl, x, v, w, dcoef, out, P, F);
-        }
-    }
-    if (P.repg) throw vm_error(VM_ERR_UNSUPPORTED, "internal: replicated gather table requested for a deposit variant without it");
-    launch_pass_depth<K, VAR, MODE, SPLIT, POW2, U0, 1024, false>(ctx, pl, x, v, w, dcoef, out, P, F);
 }
 
 template <int K, int MODE>
@@ -369,6 +400,9 @@ void launch_pass_var(vm_ctx* ctx, const DepositPlan& pl, double* x, double* v, c
             break;
         case VAR_MATCH: VM_PASS_VAR(VAR_MATCH, false); break;
         case VAR_XOR: VM_PASS_VAR(VAR_XOR, false); break;
+        case VAR_AF:
+            if (pow2) { VM_PASS_VAR(VAR_AF, true); } else { VM_PASS_VAR(VAR_AF, false); }
+            break;
         default: VM_PASS_VAR(VAR_ATOMIC, false); break;
     }
 #undef VM_PASS_VAR

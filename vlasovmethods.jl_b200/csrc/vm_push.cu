@@ -227,6 +227,21 @@ bool want_bankq(vm_ctx* ctx, int n, int deposit_mode)
     return ctx->bankq > 0 ? n >= 8 : n >= VM_BQ_MIN_N;
 }
 
+// Meshes from this size on run the limb-atomic fixed-point pass (VAR_AF, vm_deposit.cuh) in the default deposit mode:
+// its cost does not depend on the mesh size, the lane-private replicas below it are cheaper while >= 12 warps fit.
+// Tuning key "af": 0 = this rule, 1 = always (n >= 8), -1 = never (the bank-sorted / round-1 layouts).
+#ifndef VM_AF_MIN_N
+#define VM_AF_MIN_N 88
+#endif
+bool want_af(vm_ctx* ctx, int n, int deposit_mode)
+{
+    if (ctx->af < 0 || ctx->bankq > 0) return false;
+    if (deposit_mode == VM_DEPOSIT_FIXED) return n >= 8;      // (the caller prefers a shallow lane-private plan when one exists)
+    if (deposit_mode != VM_DEPOSIT_DETERMINISTIC) return false;
+    if (ctx->ctas_per_sm > 0 || ctx->threads_per_cta > 0 || ctx->replicas > 0 || ctx->force_match) return false;   // hand-tuned round-1 variants
+    return ctx->af > 0 ? n >= 8 : n >= VM_AF_MIN_N;
+}
+
 void launch_pass(vm_ctx* ctx, int mode, int order, const DepositPlan& pl, double* x, double* v, const double* w,
                  const double* dcoef, double* out, const PassParams& P, const FinishParams& F)
 {
@@ -317,16 +332,18 @@ static void pass_with_deposit(vm_field* f, vm_particles* p, int pass_mode, int d
     P.uw = vm_particles_uniform_weight(p, &P.w0) ? 1 : 0;
     BqPlan bp{};
     DepositPlan pl{};
-    bool bq = false;
+    bool bq = false, af = false;
     const bool fixed = deposit_mode == VM_DEPOSIT_FIXED;
+    PassPlan afp{};
     if (fixed) {
         // order-independent fixed-point accumulation: the shallow lane-private pass where it is the plan (small meshes),
-        // the bank-sorted pass otherwise; same bits either way (and for any launch geometry / GPU count)
+        // limb atomics (or, tuning af = -1 / bankq = 1, the bank-sorted pass) otherwise; same bits in every layout (and
+        // for any launch geometry / GPU count)
         const int S = vm_particles_fixed_scale(p);
         P.fixscale = ldexp(1.0, S);
         PassPlan pp{};
         bool priv = false;
-        if (ctx->bankq <= 0) {
+        if (ctx->bankq <= 0 && ctx->af <= 0) {
             try {
                 pp = plan_pass(ctx, n, f->order, pass_mode, VM_DEPOSIT_DETERMINISTIC);
                 const PassTier t = vm_pass_tier(pass_mode, pp.pl.var, pp.pl.threads * (pp.pl.grid / ctx->sm_count), ctx->pairs);
@@ -335,13 +352,23 @@ static void pass_with_deposit(vm_field* f, vm_particles* p, int pass_mode, int d
         }
         if (priv) { pl = pp.pl; P.repg = pp.repg ? 1 : 0; }
         else {
-            bq = n >= 8 && plan_bq(ctx, n, f->order, pass_mode, P.uw != 0, &bp);
-            if (!bq) throw vm_error(VM_ERR_UNSUPPORTED, "VM_DEPOSIT_FIXED: no fixed-point deposit layout for this mesh size / tuning");
+            af = want_af(ctx, n, deposit_mode) && plan_af(ctx, n, f->order, pass_mode, &afp);
+            if (!af) bq = n >= 8 && plan_bq(ctx, n, f->order, pass_mode, P.uw != 0, &bp);
+            if (!af && !bq) throw vm_error(VM_ERR_UNSUPPORTED, "VM_DEPOSIT_FIXED: no fixed-point deposit layout for this mesh size / tuning");
         }
     } else {
-        bq = want_bankq(ctx, n, deposit_mode) && plan_bq(ctx, n, f->order, pass_mode, P.uw != 0, &bp);
+        if (want_af(ctx, n, deposit_mode) && plan_af(ctx, n, f->order, pass_mode, &afp)) {
+            // the default mode on larger meshes IS the fixed-point sum (bit-reproducible for any geometry, <= 2^-S absolute
+            // per contribution); weights without a finite scale keep the fp64 layouts
+            const int S = vm_particles_fixed_scale(p);
+            if (p->fix_ok) { af = true; P.fixscale = ldexp(1.0, S); }
+        }
+        if (!af) bq = want_bankq(ctx, n, deposit_mode) && plan_bq(ctx, n, f->order, pass_mode, P.uw != 0, &bp);
     }
-    if (bq) {          // bank-sorted pass: one CTA per SM, one replica grid per warp
+    if (af) {          // limb atomics: one two-limb grid per CTA
+        pl = afp.pl;
+        P.repg = afp.repg ? 1 : 0;
+    } else if (bq) {   // bank-sorted pass: one CTA per SM, one replica grid per warp
         pl.var = VAR_MATCH; pl.rep_log2 = 0; pl.grid = ctx->sm_count; pl.threads = bp.warps * 32; pl.smem = bp.smem;
     } else if (!fixed) {
         const PassPlan pp = plan_pass(ctx, n, f->order, pass_mode, deposit_mode);
@@ -358,7 +385,8 @@ static void pass_with_deposit(vm_field* f, vm_particles* p, int pass_mode, int d
     } else {
         const int ngroups = (pl.grid + VM_GROUP_CTAS - 1) / VM_GROUP_CTAS;
         out = vm_partials(ctx, (size_t)(pl.grid + ngroups) * ncols);
-        const size_t gdoubles = ((size_t)(n + f->order - 1) << pl.rep_log2) * (size_t)(pl.threads / 32);
+        const size_t gdoubles = af ? vm_af_core_doubles(n, f->order)
+                                   : ((size_t)(n + f->order - 1) << pl.rep_log2) * (size_t)(pl.threads / 32);
         const bool xchg = want_solve && ctx->nranks > 1 && ctx->peers_connected && n <= VM_X_MAX_N;
         F.ticket = ctx->ticket;
         F.rhs = f->rhs; F.G = f->G; F.phi = f->phi; F.dcoef = f->dcoef; F.inv_h = f->map.inv_h;
@@ -378,6 +406,12 @@ static void pass_with_deposit(vm_field* f, vm_particles* p, int pass_mode, int d
             if (F.mode == FINISH_NONE) throw vm_error(VM_ERR_UNSUPPORTED, "VM_DEPOSIT_FIXED needs the fused finish (n_basis <= 1024, tuning no_fuse = 0)");
             if (ctx->nranks > 1 && want_solve && !F.xchg) throw vm_error(VM_ERR_UNSUPPORTED, "VM_DEPOSIT_FIXED across ranks needs the peer-memory exchange (vm_ctx_peer_connect)");
             F.fixed = 1;
+            F.inv_scale = 1.0 / P.fixscale;
+        } else if (af) {
+            // default mode on the limb-atomic layout: integer sums as far as the fused finish reaches (CTA rows, and the
+            // ranks when the peer exchange runs), one conversion to fp64 at its end; without a fused finish every CTA row
+            // is converted by the pass itself
+            F.fixed = F.mode != FINISH_NONE ? 1 : 0;
             F.inv_scale = 1.0 / P.fixscale;
         }
     }
@@ -429,6 +463,18 @@ int vm_pass_plan_query(int sm_count, size_t smem_optin_bytes, int n_basis, int o
         dev.smem_optin = smem_optin_bytes;
         const int mode = pass == 0 ? MODE_DEPOSIT : (pass == 1 ? MODE_PUSH_DEPOSIT : MODE_DRIFT_DEPOSIT);
         BqPlan bp{};
+        PassPlan afp{};
+        if (want_af(&dev, n_basis, deposit_mode) && plan_af(&dev, n_basis, order, mode, &afp)) {
+            out->variant = VAR_AF;
+            out->replicas = 1;
+            out->grid = afp.pl.grid;
+            out->threads = afp.pl.threads;
+            out->pairs = mode == MODE_DEPOSIT ? 2 : 1;
+            out->max_threads = 1024;
+            out->gather_copies = afp.repg ? VM_GATHER_COPIES : 1;
+            out->smem_bytes = afp.pl.smem;
+            return VM_OK;
+        }
         if (want_bankq(&dev, n_basis, deposit_mode) && plan_bq(&dev, n_basis, order, mode, true, &bp)) {
             out->variant = 4;
             out->replicas = 1;
