@@ -73,7 +73,9 @@ int vm_ctx_device_info(vm_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor,
  *      "pairs" (0 = auto, 1, 2, 4, 8): pairs of particles in flight per thread in the lane-private passes;
  *      "priv_min_warps" (0 = auto): fewest warps per SM for which the lane-private deposit is still chosen;
  *      "no_repg" (1: single field table in the fused pass instead of 16 bank-conflict-free copies);
- *      "bankq" (bank-sorted large-mesh pass: 0 = auto, from 256 cells; 1 = always; -1 = never);
+ *      "af" (limb-atomic fixed-point pass, the default layout of larger meshes: 0 = auto -- fused step from 44 cells,
+ *      deposit-only pass from 88 --, 1 = always, -1 = never), "af_ctas" (its CTAs per SM: 0 = auto, 1, 2, 4);
+ *      "bankq" (bank-sorted pass, the layout "af" replaced: 0 = auto -- from 88 cells when af = -1 --, 1 = always, -1 = never);
  *      "force_match" (1: MATCH.ANY grouping instead of xor-shuffle rounds), "no_uniform_w" (1: always stream the
  *      weight array), "no_pdl" (1: no programmatic dependent launch), "no_fuse" (1: separate reduce / solve kernels);
  *      "profile" (see vm_profile_read). */
@@ -171,9 +173,11 @@ int vm_field_set_coefficients(vm_field* f, const double* host_n);
 int vm_field_get_stencils(vm_field* f, double* mass_k, double* stiff_k);
 
 typedef enum vm_deposit_mode {
-    VM_DEPOSIT_DETERMINISTIC = 0, /* warp-private replicas, in-warp sort-by-cell segmented
-                                     reduce in lane order, fixed-order tree across warps/CTAs:
-                                     bit-reproducible run to run */
+    VM_DEPOSIT_DETERMINISTIC = 0, /* bit-reproducible run to run.  Small meshes: lane-private replica grids, fixed-order
+                                     tree across warps / CTAs / ranks.  Larger meshes (fused step from 44 cells,
+                                     deposit-only pass from 88): the fixed-point sum of VM_DEPOSIT_FIXED accumulated
+                                     with native 32-bit shared-memory atomics (two limbs, exact carry) -- an integer
+                                     sum, so the bits do not depend on the order the atomics land in */
     VM_DEPOSIT_ATOMIC = 1,        /* warp-aggregated shared-memory atomics + global fp64 RED */
     VM_DEPOSIT_FIXED = 2          /* order-independent: every contribution w B_j(x) is rounded once to a 64-bit
                                      fixed-point integer (scale 2^S from an exact bound on sum |w|) and all sums --
@@ -191,7 +195,8 @@ int vm_deposit(vm_field* f, vm_particles* p, int mode);
  * opt-in shared memory per CTA (B200: 148, 232448).  pass: 0 = deposit only (vm_deposit), 1 = fused
  * kick+drift+deposit step (vm_vp_run), 2 = drift+deposit prologue. */
 typedef struct vm_pass_plan {
-    int variant;        /* 0 lane-private replicas, 1 MATCH.ANY grouping, 2 shared atomics, 3 xor-shuffle, 4 bank-sorted queues */
+    int variant;        /* 0 lane-private replicas, 1 MATCH.ANY grouping, 2 shared atomics, 3 xor-shuffle, 4 bank-sorted queues,
+                           5 limb atomics (64-bit fixed point as two 32-bit words, native shared-memory adds with exact carry) */
     int replicas;       /* replica grids per warp (per CTA for variant 2) */
     int grid, threads;  /* CTAs, threads per CTA */
     int pairs;          /* pairs of particles in flight per thread */

@@ -130,9 +130,15 @@ def test_pass_plans_fit_the_device_for_every_mesh_size(vm, order):
             assert regs >= {1: 64, 2: 64, 4: 128, 8: 255}[p.pairs], what
             warps = p.threads // 32
             rows = n + order - 1
-            grids = rows * p.replicas * 8 * (1 if p.variant == 2 else warps)
+            grids = rows * p.replicas * 8 * (1 if p.variant in (2, 5) else warps)
             table = (n + order) * 8 * p.gather_copies if pass_ == 1 else 0
             assert p.smem_bytes >= grids + table + p.threads * 8, what
+            if p.variant == 5:                # limb atomics: ONE two-limb grid per CTA, whose words double as the finish's work area
+                assert p.replicas == 1 and p.pairs == (2 if pass_ == 0 else 1) and p.max_threads == 1024, what
+                assert p.smem_bytes >= max(rows, 3 * n + 2) * 8 + table + p.threads * 8, what
+                assert p.gather_copies in (1, 16) and (pass_ == 1 or p.gather_copies == 1), what
+                assert n >= (88 if pass_ == 0 else 44), what
+                continue
             if p.variant == 4:                # bank-sorted pass: one replica per warp + 32 class queues of 16 words per warp
                 assert p.replicas == 1 and ctas == 1 and p.pairs == 1 and warps >= 4, what
                 assert p.smem_bytes >= grids + table + p.threads * 8 + warps * 32 * 16 * 8, what
@@ -158,14 +164,17 @@ def test_pass_plans_of_the_benchmarked_meshes(vm):
     assert (p.variant, p.grid, p.threads, p.pairs, p.gather_copies) == (0, 296, 512, 1, 1)
     p = L.pass_plan(32, 4, 1)
     assert (p.variant, p.grid, p.threads, p.pairs, p.gather_copies) == (0, 148, 768, 1, 16)
-    p = L.pass_plan(64, 4, 1)
-    assert (p.variant, p.grid, p.threads, p.pairs, p.max_threads, p.gather_copies) == (0, 148, 384, 4, 448, 16)
-    p = L.pass_plan(80, 4, 1)                             # the last mesh with a lane-private plan (VM_BQ_MIN_N = 88)
-    assert (p.variant, p.grid, p.threads, p.pairs, p.max_threads, p.gather_copies) == (0, 148, 320, 4, 448, 16)
-    p = L.pass_plan(128, 4, 1)                            # bank-sorted queues from 88 cells on (profiles/r02_bankq_threshold.jsonl)
-    assert (p.variant, p.grid, p.threads, p.pairs, p.max_threads, p.gather_copies) == (4, 148, 1024, 1, 1024, 16)
-    assert L.pass_plan(128, 4, 0).variant == 4 and L.pass_plan(88, 4, 1).variant == 4
-    assert L.pass_plan(256, 4, 1).variant == 4 and L.pass_plan(1024, 4, 1).variant == 4
+    p = L.pass_plan(64, 4, 2)                             # (the deep lane-private tier of the mid-size meshes now only runs with af = -1)
+    p = L.pass_plan(40, 4, 1)                             # the last benchmarked mesh whose fused step runs lane-private (VM_AF_MIN_N = 44)
+    assert (p.variant, p.grid, p.pairs, p.gather_copies) == (0, 148, 1, 16)
+    p = L.pass_plan(80, 4, 0)                             # deposit-only: lane-private while a plan exists (VM_AF_MIN_N_DEPOSIT = 88)
+    assert (p.variant, p.grid, p.threads, p.pairs, p.max_threads) == (0, 148, 320, 4, 512)
+    # limb atomics (variant 5) above: one full CTA per SM, 16-fold gather table, any mesh size (profiles/r02b_af_ab.txt)
+    for n in (48, 64, 128, 256, 1024):
+        p = L.pass_plan(n, 4, 1)
+        assert (p.variant, p.grid, p.threads, p.pairs, p.max_threads, p.gather_copies) == (5, 148, 1024, 1, 1024, 16), n
+    assert L.pass_plan(64, 4, 0).variant == 0 and L.pass_plan(128, 4, 0).variant == 5 and L.pass_plan(1024, 4, 0).variant == 5
+    assert L.pass_plan(4096, 4, 1).variant == 5 and L.pass_plan(4096, 4, 1).gather_copies == 1     # 16 copies no longer fit
     assert L.pass_plan(16, 4, 0, 1).variant == 2          # VM_DEPOSIT_ATOMIC: the warp-aggregated A/B variant
     for bad in ((0, 4, 1), (16, 7, 1), (16, 4, 3), (5000, 4, 1)):
         with pytest.raises(vm.VMError):

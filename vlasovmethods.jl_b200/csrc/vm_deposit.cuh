@@ -15,6 +15,10 @@ enum { VAR_PRIV = 0, VAR_MATCH = 1, VAR_ATOMIC = 2, VAR_XOR = 3, VAR_AF = 5 };  
 // from an exact, sharding-independent bound on sum |w|) and all further additions -- replica grids, CTA rows, ranks --
 // are integer additions, which commute: the deposited vector has the same bits for every launch geometry, deposit
 // layout and number of GPUs.  The accumulators live in the same 8-byte words as the fp64 ones (bit patterns).
+#ifndef VM_AF_SKIP0
+#define VM_AF_SKIP0 0     // 1: limb-atomic layout without the high-limb atomic in lanes whose high limb + carry is zero -- fewer bank-conflict
+                          // replays, but ptxas turns the predicated red into a branch per tap: measured 5 % SLOWER (profiles/r02b_af_ab.txt)
+#endif
 #define VM_FIX_MAGIC 6755399441055744.0      // 1.5 * 2^52: fma(v, scale, MAGIC) holds rint(v * scale) in its low mantissa bits
 __device__ __forceinline__ long long fix_of(double v, double scale)          // |v * scale| < 2^51
 {
@@ -53,18 +57,32 @@ __device__ __forceinline__ void scatter(double* __restrict__ wg, int rep_log2, i
         // atoms.cu): 21 clocks per warp of particles for the 8 atomics of a cubic deposit on random rows, any mesh size
         // (the un-handled LDS/DADD/STS form on one replica: 36-40).  wg = lo words, rep = word offset of the hi array.
         if (active) {
-            unsigned* lo = (unsigned*)wg + b0;
+            const unsigned s_lo = (unsigned)__cvta_generic_to_shared(wg) + ((unsigned)b0 << 2);
+            const unsigned s_hi = s_lo + ((unsigned)rep << 2);
+            unsigned xl[K], xh[K], old[K];
 #pragma unroll
             for (int j = 0; j < K; ++j) {
                 // fix_of by limbs: the low word of the magic constant is zero, so the low limb is the low word of the
                 // fma itself and only the high word needs the subtraction
                 const double r = fma(val[j], fixscale, VM_FIX_MAGIC);
-                const unsigned xl = (unsigned)__double2loint(r);
-                const unsigned xh = (unsigned)__double2hiint(r) - 0x43380000u;
-                const unsigned old = atomicAdd(lo + j, xl);
-                unsigned t, h;
-                asm("add.cc.u32 %0, %2, %3;\n\taddc.u32 %1, %4, 0;" : "=r"(t), "=r"(h) : "r"(old), "r"(xl), "r"(xh));
-                atomicAdd(lo + rep + j, h);
+                xl[j] = (unsigned)__double2loint(r);
+                xh[j] = (unsigned)__double2hiint(r) - 0x43380000u;
+            }
+#pragma unroll
+            for (int j = 0; j < K; ++j)          // the K returning atomics in flight together
+                asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old[j]) : "r"(s_lo + 4u * j), "r"(xl[j]) : "memory");
+#pragma unroll
+            for (int j = 0; j < K; ++j) {
+#if VM_AF_SKIP0
+                asm volatile("{\n\t.reg .pred p;\n\t.reg .u32 t, h;\n\t"
+                             "add.cc.u32 t, %1, %2;\n\taddc.u32 h, %3, 0;\n\t"
+                             "setp.ne.u32 p, h, 0;\n\t@p red.shared.add.u32 [%0], h;\n\t}"
+                             :: "r"(s_hi + 4u * j), "r"(old[j]), "r"(xl[j]), "r"(xh[j]) : "memory");
+#else
+                asm volatile("{\n\t.reg .u32 t, h;\n\t"
+                             "add.cc.u32 t, %1, %2;\n\taddc.u32 h, %3, 0;\n\tred.shared.add.u32 [%0], h;\n\t}"
+                             :: "r"(s_hi + 4u * j), "r"(old[j]), "r"(xl[j]), "r"(xh[j]) : "memory");
+#endif
             }
         }
         return;

@@ -188,7 +188,11 @@ k_vp_pass(double* __restrict__ x, double* __restrict__ v, const double* __restri
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const unsigned q = q0 + u * stride;
-                const bool active = q < npairs;
+                bool active = q < npairs;
+                if constexpr (VAR == VAR_AF) {          // nothing warp-collective in this layout: idle threads skip the pair
+                    if (!active) continue;
+                    active = true;
+                }
                 process<K, VAR, MODE, SPLIT, POW2, REPG, FIXED>(buf[u].x.x, buf[u].v.x, buf[u].w.x, active, P, dsh, wg, rep, lane);
                 process<K, VAR, MODE, SPLIT, POW2, REPG, FIXED>(buf[u].x.y, buf[u].v.y, buf[u].w.y, active, P, dsh, wg, rep, lane);
                 if (active && MODE != MODE_DEPOSIT) {
@@ -280,15 +284,15 @@ inline PassPlan plan_pass(vm_ctx* ctx, int n, int order, int pass_mode, int depo
 }
 
 // Limb-atomic pass (VAR_AF): one grid of (n + K - 1) two-limb rows per CTA -- shared memory is no constraint, so the
-// CTA shape is that of the small-mesh pass (1024 threads per SM, two CTAs when two gather tables fit) and the gather
-// table is stored 16-fold whenever it fits.  ctas_req / threads_req: tuning keys af_ctas (0 = auto).
+// CTA shape is one full CTA per SM (1024 threads; tuning key af_ctas: 2 or 4 smaller ones) and the gather table is stored
+// 16-fold whenever it fits.
 inline size_t vm_af_core_doubles(int n, int order) { return (size_t)((3 * n + 2 > n + order - 1) ? 3 * n + 2 : n + order - 1); }
 inline bool plan_af(vm_ctx* ctx, int n, int order, int pass_mode, PassPlan* out)
 {
     const size_t sm_total = 227 * 1024;
     for (int rg = 1; rg >= 0; --rg) {
         if (rg && (pass_mode != MODE_PUSH_DEPOSIT || n <= 16 || ctx->no_repg)) continue;
-        for (int ctas = (ctx->af_ctas > 0 ? ctx->af_ctas : 2); ctas >= 1; --ctas) {
+        for (int ctas = (ctx->af_ctas > 0 ? ctx->af_ctas : 1); ctas >= 1; --ctas) {    // (1 x 1024 measured >= 2 x 512 from 96 cells on, equal below)
             const int threads = 1024 / ctas;
             const size_t table = pass_mode == MODE_PUSH_DEPOSIT ? vm_gather_table_doubles(n, order, rg != 0) : 0;
             const size_t smem = (table + vm_af_core_doubles(n, order) + (size_t)threads) * sizeof(double);

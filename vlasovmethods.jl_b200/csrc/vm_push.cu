@@ -227,19 +227,24 @@ bool want_bankq(vm_ctx* ctx, int n, int deposit_mode)
     return ctx->bankq > 0 ? n >= 8 : n >= VM_BQ_MIN_N;
 }
 
-// Meshes from this size on run the limb-atomic fixed-point pass (VAR_AF, vm_deposit.cuh) in the default deposit mode:
-// its cost does not depend on the mesh size, the lane-private replicas below it are cheaper while >= 12 warps fit.
+// Meshes from this size on run the limb-atomic fixed-point pass (VAR_AF, vm_deposit.cuh) in the default deposit mode.
+// Its cost does not depend on the mesh size (bound by the shared-memory data pipe: ~45 wavefronts per warp of particles);
+// the lane-private replicas below it are cheaper while enough warps fit next to them.  Measured crossover, interleaved A/B
+// on one box (profiles/r02b_af_ab.txt): fused step 40 cells 0.688 (lane-private) vs 0.677, 48 cells 0.649 vs 0.709; the
+// deposit-only pass (8-16 B/particle, the atomics are all of its work) only where no lane-private plan exists.
 // Tuning key "af": 0 = this rule, 1 = always (n >= 8), -1 = never (the bank-sorted / round-1 layouts).
 #ifndef VM_AF_MIN_N
-#define VM_AF_MIN_N 88
+#define VM_AF_MIN_N 44
 #endif
-bool want_af(vm_ctx* ctx, int n, int deposit_mode)
+#define VM_AF_MIN_N_DEPOSIT 88
+bool want_af(vm_ctx* ctx, int n, int deposit_mode, int pass_mode)
 {
     if (ctx->af < 0 || ctx->bankq > 0) return false;
     if (deposit_mode == VM_DEPOSIT_FIXED) return n >= 8;      // (the caller prefers a shallow lane-private plan when one exists)
     if (deposit_mode != VM_DEPOSIT_DETERMINISTIC) return false;
     if (ctx->ctas_per_sm > 0 || ctx->threads_per_cta > 0 || ctx->replicas > 0 || ctx->force_match) return false;   // hand-tuned round-1 variants
-    return ctx->af > 0 ? n >= 8 : n >= VM_AF_MIN_N;
+    if (ctx->af > 0) return n >= 8;
+    return n >= (pass_mode == MODE_DEPOSIT ? VM_AF_MIN_N_DEPOSIT : VM_AF_MIN_N);
 }
 
 void launch_pass(vm_ctx* ctx, int mode, int order, const DepositPlan& pl, double* x, double* v, const double* w,
@@ -352,12 +357,12 @@ static void pass_with_deposit(vm_field* f, vm_particles* p, int pass_mode, int d
         }
         if (priv) { pl = pp.pl; P.repg = pp.repg ? 1 : 0; }
         else {
-            af = want_af(ctx, n, deposit_mode) && plan_af(ctx, n, f->order, pass_mode, &afp);
+            af = want_af(ctx, n, deposit_mode, pass_mode) && plan_af(ctx, n, f->order, pass_mode, &afp);
             if (!af) bq = n >= 8 && plan_bq(ctx, n, f->order, pass_mode, P.uw != 0, &bp);
             if (!af && !bq) throw vm_error(VM_ERR_UNSUPPORTED, "VM_DEPOSIT_FIXED: no fixed-point deposit layout for this mesh size / tuning");
         }
     } else {
-        if (want_af(ctx, n, deposit_mode) && plan_af(ctx, n, f->order, pass_mode, &afp)) {
+        if (want_af(ctx, n, deposit_mode, pass_mode) && plan_af(ctx, n, f->order, pass_mode, &afp)) {
             // the default mode on larger meshes IS the fixed-point sum (bit-reproducible for any geometry, <= 2^-S absolute
             // per contribution); weights without a finite scale keep the fp64 layouts
             const int S = vm_particles_fixed_scale(p);
@@ -464,7 +469,7 @@ int vm_pass_plan_query(int sm_count, size_t smem_optin_bytes, int n_basis, int o
         const int mode = pass == 0 ? MODE_DEPOSIT : (pass == 1 ? MODE_PUSH_DEPOSIT : MODE_DRIFT_DEPOSIT);
         BqPlan bp{};
         PassPlan afp{};
-        if (want_af(&dev, n_basis, deposit_mode) && plan_af(&dev, n_basis, order, mode, &afp)) {
+        if (want_af(&dev, n_basis, deposit_mode, mode) && plan_af(&dev, n_basis, order, mode, &afp)) {
             out->variant = VAR_AF;
             out->replicas = 1;
             out->grid = afp.pl.grid;
