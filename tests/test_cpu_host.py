@@ -134,9 +134,12 @@ def test_pass_plans_fit_the_device_for_every_mesh_size(vm, order):
             table = (n + order) * 8 * p.gather_copies if pass_ == 1 else 0
             assert p.smem_bytes >= grids + table + p.threads * 8, what
             if p.variant == 5:                # limb atomics: ONE two-limb grid per CTA, whose words double as the finish's work area
-                assert p.replicas == 1 and p.pairs == (2 if pass_ == 0 else 1) and p.max_threads == 1024, what
-                assert p.smem_bytes >= max(rows, 3 * n + 2) * 8 + table + p.threads * 8, what
+                assert p.replicas in (1, 2, 4, 8, 16, 32) and p.pairs == (2 if pass_ == 0 else 1) and p.max_threads == 1024, what
+                pitch = rows + ((32 // p.replicas) % 32 - rows) % 32      # replica r is shifted by r * 32/R banks
+                assert pitch >= rows and pitch % 32 == (32 // p.replicas) % 32, what
+                assert p.smem_bytes >= max(pitch * p.replicas, 3 * n + 2) * 8 + table + p.threads * 8, what
                 assert p.gather_copies in (1, 16) and (pass_ == 1 or p.gather_copies == 1), what
+                assert p.gather_copies == 1 or p.replicas >= 8, what          # fewer replicas: the 16-fold table goes first
                 assert n >= (88 if pass_ == 0 else 44), what
                 continue
             if p.variant == 4:                # bank-sorted pass: one replica per warp + 32 class queues of 16 words per warp
@@ -173,6 +176,7 @@ def test_pass_plans_of_the_benchmarked_meshes(vm):
     for n in (48, 64, 128, 256, 1024):
         p = L.pass_plan(n, 4, 1)
         assert (p.variant, p.grid, p.threads, p.pairs, p.max_threads, p.gather_copies) == (5, 148, 1024, 1, 1024, 16), n
+        assert p.replicas == (32 if n <= 512 else 8), n      # bank-steered replicas: conflict-free atomics up to 512 cells
     assert L.pass_plan(64, 4, 0).variant == 0 and L.pass_plan(128, 4, 0).variant == 5 and L.pass_plan(1024, 4, 0).variant == 5
     assert L.pass_plan(4096, 4, 1).variant == 5 and L.pass_plan(4096, 4, 1).gather_copies == 1     # 16 copies no longer fit
     assert L.pass_plan(16, 4, 0, 1).variant == 2          # VM_DEPOSIT_ATOMIC: the warp-aggregated A/B variant

@@ -11,7 +11,7 @@ N = int(sys.argv[1]) if len(sys.argv) > 1 else 100_000_000
 meshes = [int(a) for a in sys.argv[2:]] or [16, 32, 64, 128, 256, 512, 1024]
 L = 2 * math.pi / 0.3
 PEAK = json.load(open('MEASURED_PEAKS.json'))['hbm_gbs']
-variants = [("base", {"af": -1}), ("af", {"af": 1}), ("af_1cta", {"af": 1, "af_ctas": 1}), ("af_norepg", {"af": 1, "no_repg": 1})]
+variants = [("base", {"af": -1}), ("af", {"af": 1}), ("af_r8", {"af": 1, "af_replicas": 8}), ("af_r1", {"af": 1, "af_replicas": 1}), ("af_2cta", {"af": 1, "af_ctas": 2})]
 ref = {}
 for name, tun in variants:
     ctx = vm.Context(0)

@@ -290,6 +290,10 @@ int vm_ctx_set_tuning(vm_ctx* ctx, const char* key, int value)
     }
     else if (k == "bankq") { VM_REQUIRE(value >= -1 && value <= 1, "bankq must be -1, 0 or 1"); ctx->bankq = value; }
     else if (k == "af") { VM_REQUIRE(value >= -1 && value <= 1, "af must be -1, 0 or 1"); ctx->af = value; }
+    else if (k == "af_replicas") {
+        VM_REQUIRE(value == 0 || (value >= 1 && value <= 32 && (value & (value - 1)) == 0), "af_replicas must be a power of two <= 32");
+        ctx->af_replicas = value;
+    }
     else if (k == "af_ctas") { VM_REQUIRE(value >= 0 && value <= 4 && value != 3, "af_ctas must be 0, 1, 2 or 4"); ctx->af_ctas = value; }
     else if (k == "no_repg") ctx->no_repg = value;   // 1: single (bank-conflicting) gather table in the fused pass (A/B)
     else if (k == "profile") ctx->profile = value;

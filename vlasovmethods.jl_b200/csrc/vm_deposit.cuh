@@ -8,6 +8,14 @@
 #pragma once
 #include "vm_internal.cuh"
 
+// Row pitch (32-bit words) of one replica of the limb-atomic layout (VAR_AF): the smallest pitch >= rows that is congruent
+// to 32/R modulo 32, so that replica r is shifted by r * 32/R banks against replica 0.
+__host__ __device__ inline int vm_af_pitch(int rows, int rep_log2)
+{
+    const int want = (32 >> rep_log2) & 31;
+    return rows + ((want - rows) & 31);
+}
+
 enum { VAR_PRIV = 0, VAR_MATCH = 1, VAR_ATOMIC = 2, VAR_XOR = 3, VAR_AF = 5 };   // (4 is the bank-sorted pass in vm_pass_plan.variant)
 
 // ------------------------------------------------ order-independent sums -----
@@ -47,18 +55,23 @@ __device__ __forceinline__ void scatter(double* __restrict__ wg, int rep_log2, i
     static_assert(!FIXED || VAR == VAR_PRIV || VAR == VAR_AF, "fixed-point accumulation exists in the lane-private, bank-sorted and limb-atomic layouts");
     static_assert(FIXED || VAR != VAR_AF, "the limb-atomic layout accumulates fixed-point integers");
     if (VAR == VAR_AF) {
-        // ONE grid per CTA for all warps, each row a 64-bit fixed-point integer stored as two 32-bit limbs in two
-        // arrays (lo[rows] then hi[rows]: consecutive rows in consecutive banks).  64-bit and fp64 shared-memory
-        // atomics are CAS loops on sm_100a (ATOMS.CAST.SPIN), 32-bit integer adds are native (ATOMS.ADD): add the low
-        // limb with a returning atomic, derive the carry from the returned value, add high limb + carry with a second
-        // one.  Every limb update is atomic and every wrap of a low limb is carried exactly once by the thread that
-        // caused it, so after all adds (hi:lo) is the exact sum mod 2^64 in ANY order; collisions and bank conflicts
-        // are serialised by the hardware, no replicas, no sorting, no warp-collective step.  Measured (tools/microbench/
-        // atoms.cu): 21 clocks per warp of particles for the 8 atomics of a cubic deposit on random rows, any mesh size
-        // (the un-handled LDS/DADD/STS form on one replica: 36-40).  wg = lo words, rep = word offset of the hi array.
+        // Grids shared by ALL warps of the CTA, each row a 64-bit fixed-point integer stored as two 32-bit limbs in two
+        // arrays (lo[] then hi[]: consecutive rows in consecutive banks).  64-bit and fp64 shared-memory atomics are CAS
+        // loops on sm_100a (ATOMS.CAST.SPIN), 32-bit integer adds are native (ATOMS.ADD): add the low limb with a
+        // returning atomic, derive the carry from the returned value, add high limb + carry with a second one.  Every
+        // limb update is atomic and every wrap of a low limb is carried exactly once by the thread that caused it, so
+        // after all adds (hi:lo) is the exact sum mod 2^64 in ANY order.
+        // Bank steering: R = 2^rep_log2 replicas of the grid per CTA, replica r shifted by r * 32/R banks (row pitch
+        // RP = 32/R mod 32).  Lane l deposits a particle with first row b0 into replica ((l - b0) mod 32) / (32/R): its
+        // word then sits in bank l - delta, 0 <= delta < 32/R, and tap j in bank l - delta + j.  With R = 32 the 32 lanes
+        // of every atomic hit 32 distinct banks -- ONE wavefront per instruction, no collision inside a warp ever -- the
+        // lane-private layout, but shared by all warps because the adds are atomic: 256 B per mesh cell per CTA instead
+        // of per warp.  (Measured with a single replica: 3.8 wavefronts per atomic on random rows, the pass sat at 95 %
+        // of the LSU wavefront peak; tools/microbench/atoms.cu.)  wg = lo words, rep = row pitch RP in words.
         if (active) {
-            const unsigned s_lo = (unsigned)__cvta_generic_to_shared(wg) + ((unsigned)b0 << 2);
-            const unsigned s_hi = s_lo + ((unsigned)rep << 2);
+            const unsigned r = ((unsigned)(lane - b0) & 31u) >> (5 - rep_log2);
+            const unsigned s_lo = (unsigned)__cvta_generic_to_shared(wg) + ((r * (unsigned)rep + (unsigned)b0) << 2);
+            const unsigned s_hi = s_lo + (((unsigned)rep << rep_log2) << 2);
             unsigned xl[K], xh[K], old[K];
 #pragma unroll
             for (int j = 0; j < K; ++j) {
@@ -221,16 +234,22 @@ __device__ __forceinline__ void flush_grid(double* __restrict__ grid, double* __
     }
 }
 
-// Limb-atomic layout (VAR_AF): join the limbs of every row, fold the ghost rows and emit the CTA's partial row -- as the
-// 64-bit integer itself when the fused finish continues in integers (as_bits), converted to fp64 otherwise.
+// Limb-atomic layout (VAR_AF): join the limbs of every row, sum the R replicas, fold the ghost rows and emit the CTA's
+// partial row -- as the 64-bit integer itself when the fused finish continues in integers (as_bits), converted to fp64
+// otherwise.  pitch = row pitch of a replica in words; the hi limbs follow the R * pitch lo limbs.
 __device__ __forceinline__ void flush_limbs(const unsigned* __restrict__ lo, double* __restrict__ out, int n, int ghost,
-                                            int ncols, bool as_bits, double inv_scale)
+                                            int rep_log2, int pitch, int ncols, bool as_bits, double inv_scale)
 {
-    const unsigned* hi = lo + n + ghost;
+    const int R = 1 << rep_log2;
+    const unsigned* hi = lo + (pitch << rep_log2);
     __syncthreads();
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        long long s = (long long)(((unsigned long long)hi[i] << 32) | lo[i]);
-        if (i < ghost) s += (long long)(((unsigned long long)hi[n + i] << 32) | lo[n + i]);
+        long long s = 0;
+        for (int r = 0; r < R; ++r) {
+            const int e = r * pitch + i;
+            s += (long long)(((unsigned long long)hi[e] << 32) | lo[e]);
+            if (i < ghost) s += (long long)(((unsigned long long)hi[e + n] << 32) | lo[e + n]);
+        }
         out[(size_t)blockIdx.x * ncols + i] = as_bits ? __longlong_as_double(s) : (double)s * inv_scale;
     }
     __syncthreads();

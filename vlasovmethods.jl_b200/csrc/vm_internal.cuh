@@ -57,6 +57,7 @@ struct vm_ctx {
     // tuning (0 = auto)
     int ctas_per_sm = 0, threads_per_cta = 0, replicas = 0, profile = 0, no_fuse = 0, no_pdl = 0, force_match = 0, no_uniform_w = 0;
     int bankq = 0;      // bank-sorted large-mesh pass: 0 = auto (n >= 256), 1 = always, -1 = never
+    int af_replicas = 0;       // bank-steered replicas per CTA of the limb-atomic pass (0 = as many as fit, <= 32)
     int af = 0, af_ctas = 0;   // limb-atomic fixed-point pass: 0 = auto (from VM_AF_MIN_N cells), 1 = always, -1 = never; CTAs per SM (0 = auto)
     int pairs = 0, priv_min_warps = 0, no_repg = 0;   // pairs in flight per thread / fewest warps the lane-private deposit accepts
     // per-launch event brackets of the dominant kernel (profile == 1)

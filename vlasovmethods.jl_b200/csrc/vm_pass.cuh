@@ -127,13 +127,15 @@ k_vp_pass(double* __restrict__ x, double* __restrict__ v, const double* __restri
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     double* dsh = smem;
     double* grid = smem + (MODE == MODE_PUSH_DEPOSIT ? (n + K) * (REPG ? VM_GATHER_COPIES : 1) : 0);
-    const int gsz = (VAR == VAR_AF) ? (n + GHOST) : ((n + GHOST) << P.rep_log2);     // VAR_AF: (n + GHOST) lo words + as many hi words
+    // VAR_AF: R = 2^rep_log2 bank-steered replicas of (pitch) lo words, then as many hi words: R * pitch doubles in all
+    const int pitch = vm_af_pitch(n + GHOST, P.rep_log2);
+    const int gsz = (VAR == VAR_AF) ? (pitch << P.rep_log2) : ((n + GHOST) << P.rep_log2);
     const int gtotal = (VAR == VAR_ATOMIC || VAR == VAR_AF) ? gsz : gsz * nwarps;
     // (VAR_AF: the finish needs 3n + 1 doubles of work area where the limb arrays were, see vm_af_core_doubles)
     double* scratch = grid + ((VAR == VAR_AF && 3 * n + 2 > gtotal) ? 3 * n + 2 : gtotal);
     for (int i = threadIdx.x; i < gtotal; i += blockDim.x) grid[i] = 0.0;
     double* wg = (VAR == VAR_ATOMIC || VAR == VAR_AF) ? grid : grid + warp * gsz;
-    const int rep = (VAR == VAR_AF) ? gsz : (((VAR == VAR_ATOMIC) ? warp : lane) & ((1 << P.rep_log2) - 1));
+    const int rep = (VAR == VAR_AF) ? pitch : (((VAR == VAR_ATOMIC) ? warp : lane) & ((1 << P.rep_log2) - 1));
 
     const unsigned npairs = (unsigned)(P.n >> 1);
     const unsigned stride = gridDim.x * blockDim.x;
@@ -252,7 +254,7 @@ k_vp_pass(double* __restrict__ x, double* __restrict__ v, const double* __restri
             if (MODE == MODE_PUSH_DEPOSIT) v[P.n - 1] = vp;
         }
     }
-    if (VAR == VAR_AF) flush_limbs((const unsigned*)grid, out, n, GHOST, P.ncols, F.mode != FINISH_NONE && F.fixed, F.inv_scale);
+    if (VAR == VAR_AF) flush_limbs((const unsigned*)grid, out, n, GHOST, P.rep_log2, pitch, P.ncols, F.mode != FINISH_NONE && F.fixed, F.inv_scale);
     else flush_grid<VAR, FIXED>(grid, scratch, out, n, GHOST, P.rep_log2, nwarps, P.ncols);
     if (VAR != VAR_ATOMIC && F.mode != FINISH_NONE) finish_grid(F, out, gridDim.x, n, grid, scratch);
 }
@@ -283,23 +285,32 @@ inline PassPlan plan_pass(vm_ctx* ctx, int n, int order, int pass_mode, int depo
     return pp;
 }
 
-// Limb-atomic pass (VAR_AF): one grid of (n + K - 1) two-limb rows per CTA -- shared memory is no constraint, so the
-// CTA shape is one full CTA per SM (1024 threads; tuning key af_ctas: 2 or 4 smaller ones) and the gather table is stored
-// 16-fold whenever it fits.
-inline size_t vm_af_core_doubles(int n, int order) { return (size_t)((3 * n + 2 > n + order - 1) ? 3 * n + 2 : n + order - 1); }
+// Limb-atomic pass (VAR_AF): R bank-steered replicas of a grid of (n + K - 1) two-limb rows per CTA, shared by all its
+// warps (vm_deposit.cuh) -- 8 B * R per row and CTA, so the CTA shape is one full CTA per SM (1024 threads; tuning key
+// af_ctas: 2 or 4 smaller ones), the gather table is stored 16-fold whenever it fits, and R is the largest power of
+// two <= 32 that still fits (32 up to 512 cells with the 16-fold table; tuning key "replicas" overrides it here too).
+inline size_t vm_af_core_doubles(int n, int order, int rep_log2)
+{
+    const size_t limbs = (size_t)vm_af_pitch(n + order - 1, rep_log2) << rep_log2;
+    return limbs > (size_t)(3 * n + 2) ? limbs : (size_t)(3 * n + 2);
+}
 inline bool plan_af(vm_ctx* ctx, int n, int order, int pass_mode, PassPlan* out)
 {
     const size_t sm_total = 227 * 1024;
+    int rl_max = 5;
+    if (ctx->af_replicas > 0) { rl_max = 0; while ((1 << rl_max) < ctx->af_replicas) ++rl_max; }
     for (int rg = 1; rg >= 0; --rg) {
         if (rg && (pass_mode != MODE_PUSH_DEPOSIT || n <= 16 || ctx->no_repg)) continue;
         for (int ctas = (ctx->af_ctas > 0 ? ctx->af_ctas : 1); ctas >= 1; --ctas) {    // (1 x 1024 measured >= 2 x 512 from 96 cells on, equal below)
             const int threads = 1024 / ctas;
             const size_t table = pass_mode == MODE_PUSH_DEPOSIT ? vm_gather_table_doubles(n, order, rg != 0) : 0;
-            const size_t smem = (table + vm_af_core_doubles(n, order) + (size_t)threads) * sizeof(double);
-            if (smem <= ctx->smem_optin && (size_t)ctas * (smem + 1024) <= sm_total && threads >= 128) {
-                out->pl = DepositPlan{VAR_AF, 0, ctx->sm_count * ctas, threads, smem};
-                out->repg = rg != 0;
-                return true;
+            for (int rl = rl_max; rl >= (rg ? 3 : 0); --rl) {        // (fewer than 8 replicas: rather give up the 16-fold table)
+                const size_t smem = (table + vm_af_core_doubles(n, order, rl) + (size_t)threads) * sizeof(double);
+                if (smem <= ctx->smem_optin && (size_t)ctas * (smem + 1024) <= sm_total && threads >= 128) {
+                    out->pl = DepositPlan{VAR_AF, rl, ctx->sm_count * ctas, threads, smem};
+                    out->repg = rg != 0;
+                    return true;
+                }
             }
         }
     }

@@ -390,7 +390,7 @@ static void pass_with_deposit(vm_field* f, vm_particles* p, int pass_mode, int d
     } else {
         const int ngroups = (pl.grid + VM_GROUP_CTAS - 1) / VM_GROUP_CTAS;
         out = vm_partials(ctx, (size_t)(pl.grid + ngroups) * ncols);
-        const size_t gdoubles = af ? vm_af_core_doubles(n, f->order)
+        const size_t gdoubles = af ? vm_af_core_doubles(n, f->order, pl.rep_log2)
                                    : ((size_t)(n + f->order - 1) << pl.rep_log2) * (size_t)(pl.threads / 32);
         const bool xchg = want_solve && ctx->nranks > 1 && ctx->peers_connected && n <= VM_X_MAX_N;
         F.ticket = ctx->ticket;
@@ -471,7 +471,7 @@ int vm_pass_plan_query(int sm_count, size_t smem_optin_bytes, int n_basis, int o
         PassPlan afp{};
         if (want_af(&dev, n_basis, deposit_mode, mode) && plan_af(&dev, n_basis, order, mode, &afp)) {
             out->variant = VAR_AF;
-            out->replicas = 1;
+            out->replicas = 1 << afp.pl.rep_log2;
             out->grid = afp.pl.grid;
             out->threads = afp.pl.threads;
             out->pairs = mode == MODE_DEPOSIT ? 2 : 1;
