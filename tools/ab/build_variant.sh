@@ -8,6 +8,8 @@ mkdir -p /tmp/abbuild/$1
 NV="/usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a"
 $NV -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -ccbin /usr/bin/g++ -I../../include -I. --expt-relaxed-constexpr $2 \
     -DVM_PASS_ORDER=4 -c vm_pass_order.cu -o /tmp/abbuild/$1/vm_pass_k4.o
-OBJS=$(ls build/*.o | grep -v vm_pass_k4)
-$NV -shared -ccbin /usr/bin/g++ -o ../../tools/ab/lib_$1.so $OBJS /tmp/abbuild/$1/vm_pass_k4.o -ldl
+$NV -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -ccbin /usr/bin/g++ -I../../include -I. --expt-relaxed-constexpr $2 \
+    -c vm_push.cu -o /tmp/abbuild/$1/vm_push.o          # (the host-side plan lives in the headers too)
+OBJS=$(ls build/*.o | grep -v -e vm_pass_k4 -e vm_push)
+$NV -shared -ccbin /usr/bin/g++ -o ../../tools/ab/lib_$1.so $OBJS /tmp/abbuild/$1/vm_pass_k4.o /tmp/abbuild/$1/vm_push.o -ldl
 echo built tools/ab/lib_$1.so

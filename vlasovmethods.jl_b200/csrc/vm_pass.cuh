@@ -71,12 +71,41 @@ inline size_t vm_gather_table_doubles(int n, int order, bool repg) { return (siz
 // SPLIT: two half kicks (new-API Strang) instead of one.  The fused mode always applies the two
 // separately rounded half drifts of consecutive Strang steps (drift1 then drift2).
 // Phase A of a particle: everything up to the deposit weights (reads the read-only dcoef table only).
-template <int K, int MODE, bool SPLIT, bool POW2, bool REPG, bool FIXED = false>
+// Limb-atomic pass: with conflict-free atomics it is bound by instruction issue at the sustained (power-capped) SM clock,
+// so it takes the cheaper forms the HBM-bound lane-private pass does not need.  One box, 64 / 256 / 1024 cells, fraction
+// of the HBM roofline (profiles/r02c_af_variants.txt): as first written 0.763 / 0.756 / 0.733 (255 instructions per pair
+// of particles); canonical xi without the fmin 0.770 / 0.765 / 0.739 (236); + FRND/F2I cell lookup 0.787 / 0.780 / 0.748
+// (212); + main loop unrolled over the two buffer sets (no register moves) 0.851 / 0.839 / 0.78 (196).
+#ifndef VM_AF_CONV
+#define VM_AF_CONV 1
+#endif
+#ifndef VM_AF_UNROLL
+#define VM_AF_UNROLL 1
+#endif
+#ifndef VM_AF_THREADS
+#define VM_AF_THREADS 1024      // resident threads per SM of the limb-atomic pass (A/B: 768 = 85 registers per thread)
+#endif
+#ifndef VM_AF_PAIRS
+#define VM_AF_PAIRS 1           // pairs of particles in flight per thread in its fused / drift modes (A/B)
+#endif
+#ifndef VM_AF_L2PF
+#define VM_AF_L2PF 0            // 1: prefetch.global.L2 of the lines two iterations ahead (A/B)
+#endif
+#ifndef VM_AF_FORCE_UW
+#define VM_AF_FORCE_UW 0        // 1: BENCHMARK ONLY -- assume uniform weights at compile time (what a UW instantiation would gain)
+#endif
+// The canonical xi of the fixed-point layouts is (xi + 1) - 1.  (The bank-sorted pass clamps xi below 1 first because it
+// stores the mantissa of xi + 1; for the value computed here the clamp changes nothing: it only bites at xi == 1, where
+// both forms give 1.)
+#ifndef VM_FIX_FMIN
+#define VM_FIX_FMIN 0
+#endif
+template <int K, int MODE, bool SPLIT, bool POW2, bool REPG, bool FIXED = false, bool AF = false>
 __device__ __forceinline__ void prepare(double& xp, double& vp, double wp, const PassParams& P,
                                         const double* __restrict__ dsh, int& b0, double (&val)[K])
 {
     double xi;
-    constexpr bool CONV = (MODE == MODE_DEPOSIT);      // see cell_of: measured per mode
+    constexpr bool CONV = (MODE == MODE_DEPOSIT) || (VM_AF_CONV && AF);      // see cell_of: measured per mode
     if (MODE == MODE_PUSH_DEPOSIT) {
         cell_of<CONV, POW2>(P.map, xp, b0, xi);
         const double dphi = gather_dphi<K, REPG>(dsh, b0, xi);
@@ -90,7 +119,11 @@ __device__ __forceinline__ void prepare(double& xp, double& vp, double wp, const
     if (FIXED) {
         // the fixed-point deposit must round the SAME per-particle numbers in every layout: the bank-sorted pass
         // carries xi as the 52-bit mantissa of xi + 1 (vm_pass_bq.cuh: bq_pack), so that is the canonical xi
+#if VM_FIX_FMIN
         xi = (fmin(xi, 0x1.fffffffffffffp-1) + 1.0) - 1.0;
+#else
+        xi = (xi + 1.0) - 1.0;
+#endif
     }
     bspline_uniform_w<K>(xi, wp, val);                 // inactive lanes carry wp == 0
 }
@@ -101,7 +134,7 @@ __device__ __forceinline__ void process(double& xp, double& vp, double wp, bool 
 {
     int b0;
     double val[K];
-    prepare<K, MODE, SPLIT, POW2, REPG, FIXED>(xp, vp, wp, P, dsh, b0, val);
+    prepare<K, MODE, SPLIT, POW2, REPG, FIXED, VAR == VAR_AF>(xp, vp, wp, P, dsh, b0, val);
     scatter<K, VAR, FIXED>(wg, P.rep_log2, rep, lane, b0, val, active, P.fixscale);
 }
 
@@ -148,11 +181,18 @@ k_vp_pass(double* __restrict__ x, double* __restrict__ v, const double* __restri
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const unsigned q = q0 + u * stride;
-            buf[u].w = make_double2(0., 0.);            // out-of-range pairs deposit nothing
+            if (!(VM_AF_FORCE_UW && VAR == VAR_AF)) buf[u].w = make_double2(0., 0.);            // out-of-range pairs deposit nothing
             if (q < npairs) {
                 buf[u].x = ld_stream2(x + 2 * (size_t)q);
                 if (MODE != MODE_DEPOSIT) buf[u].v = ld_stream2(v + 2 * (size_t)q);
-                buf[u].w = P.uw ? make_double2(P.w0, P.w0) : ld_stream2(w + 2 * (size_t)q);
+                if (!(VM_AF_FORCE_UW && VAR == VAR_AF)) buf[u].w = P.uw ? make_double2(P.w0, P.w0) : ld_stream2(w + 2 * (size_t)q);
+                if (VM_AF_L2PF && VAR == VAR_AF && MODE != MODE_DEPOSIT) {
+                    const size_t qq = 2 * ((size_t)q + 2 * (size_t)chunk);
+                    if (qq < 2 * (size_t)npairs) {
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(x + qq));
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(v + qq));
+                    }
+                }
             }
         }
     };
@@ -195,6 +235,7 @@ k_vp_pass(double* __restrict__ x, double* __restrict__ v, const double* __restri
                     if (!active) continue;
                     active = true;
                 }
+                if (VM_AF_FORCE_UW && VAR == VAR_AF) buf[u].w = make_double2(P.w0, P.w0);
                 process<K, VAR, MODE, SPLIT, POW2, REPG, FIXED>(buf[u].x.x, buf[u].v.x, buf[u].w.x, active, P, dsh, wg, rep, lane);
                 process<K, VAR, MODE, SPLIT, POW2, REPG, FIXED>(buf[u].x.y, buf[u].v.y, buf[u].w.y, active, P, dsh, wg, rep, lane);
                 if (active && MODE != MODE_DEPOSIT) {
@@ -218,7 +259,7 @@ k_vp_pass(double* __restrict__ x, double* __restrict__ v, const double* __restri
     if (MODE == MODE_PUSH_DEPOSIT) load_dcoef_ext<REPG>(dsh, dcoef, n, K - 2 > 0 ? K - 2 : 0);
     __syncthreads();
     if (!(MODE == MODE_PUSH_DEPOSIT && VM_PASS_EARLY_LOAD)) load(A, q);
-    if (MODE == MODE_DEPOSIT) {
+    if (MODE == MODE_DEPOSIT || (VM_AF_UNROLL && VAR == VAR_AF)) {
         // 16 B/particle pass, issue-bound: unrolled twice over the two buffer sets (no register moves)
         for (unsigned it = 0; it < iters; it += 2, q += 2 * chunk) {
             load(B, q + chunk);
@@ -302,7 +343,7 @@ inline bool plan_af(vm_ctx* ctx, int n, int order, int pass_mode, PassPlan* out)
     for (int rg = 1; rg >= 0; --rg) {
         if (rg && (pass_mode != MODE_PUSH_DEPOSIT || n <= 16 || ctx->no_repg)) continue;
         for (int ctas = (ctx->af_ctas > 0 ? ctx->af_ctas : 1); ctas >= 1; --ctas) {    // (1 x 1024 measured >= 2 x 512 from 96 cells on, equal below)
-            const int threads = 1024 / ctas;
+            const int threads = VM_AF_THREADS / ctas;
             const size_t table = pass_mode == MODE_PUSH_DEPOSIT ? vm_gather_table_doubles(n, order, rg != 0) : 0;
             for (int rl = rl_max; rl >= (rg ? 3 : 0); --rl) {        // (fewer than 8 replicas: rather give up the 16-fold table)
                 const size_t smem = (table + vm_af_core_doubles(n, order, rl) + (size_t)threads) * sizeof(double);
@@ -371,8 +412,9 @@ void launch_pass_inst(vm_ctx* ctx, const DepositPlan& pl, double* x, double* v, 
     if (pl.threads > t.max_threads) throw vm_error(VM_ERR_UNSUPPORTED, "internal: CTA larger than the launch bound of its tier");
     if constexpr (VAR == VAR_AF) {     // limb atomics: always fixed-point, shallow tier
         if (P.fixscale == 0.0) throw vm_error(VM_ERR_UNSUPPORTED, "internal: the limb-atomic deposit needs a fixed-point scale");
-        if (P.repg) return launch_pass_depth<K, VAR, MODE, SPLIT, POW2, U0, 1024, (MODE == MODE_PUSH_DEPOSIT), true>(ctx, pl, x, v, w, dcoef, out, P, F);
-        return launch_pass_depth<K, VAR, MODE, SPLIT, POW2, U0, 1024, false, true>(ctx, pl, x, v, w, dcoef, out, P, F);
+        constexpr int UA = (MODE == MODE_DEPOSIT) ? 2 : VM_AF_PAIRS;
+        if (P.repg) return launch_pass_depth<K, VAR, MODE, SPLIT, POW2, UA, VM_AF_THREADS, (MODE == MODE_PUSH_DEPOSIT), true>(ctx, pl, x, v, w, dcoef, out, P, F);
+        return launch_pass_depth<K, VAR, MODE, SPLIT, POW2, UA, VM_AF_THREADS, false, true>(ctx, pl, x, v, w, dcoef, out, P, F);
     } else {
         if (P.fixscale != 0.0) {      // fixed-point accumulation: lane-private layout, shallow tier (the planner sends everything else to the limb-atomic or bank-sorted pass)
             if constexpr (VAR == VAR_PRIV) {
