@@ -73,7 +73,7 @@ int vm_ctx_device_info(vm_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor,
  *      "pairs" (0 = auto, 1, 2, 4, 8): pairs of particles in flight per thread in the lane-private passes;
  *      "priv_min_warps" (0 = auto): fewest warps per SM for which the lane-private deposit is still chosen;
  *      "no_repg" (1: single field table in the fused pass instead of 16 bank-conflict-free copies);
- *      "af" (limb-atomic fixed-point pass, the default layout of larger meshes: 0 = auto -- fused step from 44 cells,
+ *      "af" (limb-atomic fixed-point pass, the default layout of larger meshes: 0 = auto -- fused step from 20 cells,
  *      deposit-only pass from 88 --, 1 = always, -1 = never), "af_ctas" (its CTAs per SM: 0 = auto, 1, 2, 4);
  *      "bankq" (bank-sorted pass, the layout "af" replaced: 0 = auto -- from 88 cells when af = -1 --, 1 = always, -1 = never);
  *      "force_match" (1: MATCH.ANY grouping instead of xor-shuffle rounds), "no_uniform_w" (1: always stream the
@@ -174,7 +174,7 @@ int vm_field_get_stencils(vm_field* f, double* mass_k, double* stiff_k);
 
 typedef enum vm_deposit_mode {
     VM_DEPOSIT_DETERMINISTIC = 0, /* bit-reproducible run to run.  Small meshes: lane-private replica grids, fixed-order
-                                     tree across warps / CTAs / ranks.  Larger meshes (fused step from 44 cells,
+                                     tree across warps / CTAs / ranks.  Larger meshes (fused step from 20 cells,
                                      deposit-only pass from 88): the fixed-point sum of VM_DEPOSIT_FIXED accumulated
                                      with native 32-bit shared-memory atomics (two limbs, exact carry) -- an integer
                                      sum, so the bits do not depend on the order the atomics land in */

@@ -139,8 +139,7 @@ def test_pass_plans_fit_the_device_for_every_mesh_size(vm, order):
                 assert pitch >= rows and pitch % 32 == (32 // p.replicas) % 32, what
                 assert p.smem_bytes >= max(pitch * p.replicas, 3 * n + 2) * 8 + table + p.threads * 8, what
                 assert p.gather_copies in (1, 16) and (pass_ == 1 or p.gather_copies == 1), what
-                assert p.gather_copies == 1 or p.replicas >= 8, what          # fewer replicas: the 16-fold table goes first
-                assert n >= (88 if pass_ == 0 else 44), what
+                assert n >= (88 if pass_ == 0 else 20), what
                 continue
             if p.variant == 4:                # bank-sorted pass: one replica per warp + 32 class queues of 16 words per warp
                 assert p.replicas == 1 and ctas == 1 and p.pairs == 1 and warps >= 4, what
@@ -165,18 +164,18 @@ def test_pass_plans_of_the_benchmarked_meshes(vm):
     L = vm._lib
     p = L.pass_plan(16, 4, 1)
     assert (p.variant, p.grid, p.threads, p.pairs, p.gather_copies) == (0, 296, 512, 1, 1)
-    p = L.pass_plan(32, 4, 1)
-    assert (p.variant, p.grid, p.threads, p.pairs, p.gather_copies) == (0, 148, 768, 1, 16)
-    p = L.pass_plan(64, 4, 2)                             # (the deep lane-private tier of the mid-size meshes now only runs with af = -1)
-    p = L.pass_plan(40, 4, 1)                             # the last benchmarked mesh whose fused step runs lane-private (VM_AF_MIN_N = 44)
-    assert (p.variant, p.grid, p.pairs, p.gather_copies) == (0, 148, 1, 16)
+    p = L.pass_plan(19, 4, 1)                             # the last mesh whose fused step runs lane-private (VM_AF_MIN_N = 20)
+    assert (p.variant, p.grid, p.pairs, p.gather_copies) == (0, 296, 1, 16)
+    p = L.pass_plan(64, 4, 2)                             # (the deep lane-private tiers of the mid-size meshes now only run with af = -1)
+    assert p.variant == 5
     p = L.pass_plan(80, 4, 0)                             # deposit-only: lane-private while a plan exists (VM_AF_MIN_N_DEPOSIT = 88)
     assert (p.variant, p.grid, p.threads, p.pairs, p.max_threads) == (0, 148, 320, 4, 512)
     # limb atomics (variant 5) above: one full CTA per SM, 16-fold gather table, any mesh size (profiles/r02b_af_ab.txt)
-    for n in (48, 64, 128, 256, 1024):
+    for n in (20, 32, 64, 128, 256, 1024):
         p = L.pass_plan(n, 4, 1)
-        assert (p.variant, p.grid, p.threads, p.pairs, p.max_threads, p.gather_copies) == (5, 148, 1024, 1, 1024, 16), n
-        assert p.replicas == (32 if n <= 512 else 8), n      # bank-steered replicas: conflict-free atomics up to 512 cells
+        assert (p.variant, p.grid, p.threads, p.pairs, p.max_threads) == (5, 148, 1024, 1, 1024), n
+        # bank-steered replicas: conflict-free atomics (32 replicas) with the 16-fold gather table up to 512 cells; replicas go first
+        assert (p.replicas, p.gather_copies) == ((32, 16) if n <= 512 else (16, 1)), n
     assert L.pass_plan(64, 4, 0).variant == 0 and L.pass_plan(128, 4, 0).variant == 5 and L.pass_plan(1024, 4, 0).variant == 5
     assert L.pass_plan(4096, 4, 1).variant == 5 and L.pass_plan(4096, 4, 1).gather_copies == 1     # 16 copies no longer fit
     assert L.pass_plan(16, 4, 0, 1).variant == 2          # VM_DEPOSIT_ATOMIC: the warp-aggregated A/B variant

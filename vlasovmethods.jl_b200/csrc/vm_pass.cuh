@@ -82,6 +82,12 @@ inline size_t vm_gather_table_doubles(int n, int order, bool repg) { return (siz
 #ifndef VM_AF_UNROLL
 #define VM_AF_UNROLL 1
 #endif
+#ifndef VM_PRIV_CONV
+#define VM_PRIV_CONV 0          // 1: FRND/F2I cell lookup in the fused lane-private pass too (A/B)
+#endif
+#ifndef VM_PRIV_UNROLL
+#define VM_PRIV_UNROLL 0        // 1: unrolled main loop in the shallow fused lane-private pass too (A/B)
+#endif
 #ifndef VM_AF_THREADS
 #define VM_AF_THREADS 1024      // resident threads per SM of the limb-atomic pass (A/B: 768 = 85 registers per thread)
 #endif
@@ -105,7 +111,7 @@ __device__ __forceinline__ void prepare(double& xp, double& vp, double wp, const
                                         const double* __restrict__ dsh, int& b0, double (&val)[K])
 {
     double xi;
-    constexpr bool CONV = (MODE == MODE_DEPOSIT) || (VM_AF_CONV && AF);      // see cell_of: measured per mode
+    constexpr bool CONV = (MODE == MODE_DEPOSIT) || (VM_AF_CONV && AF) || VM_PRIV_CONV;      // see cell_of: measured per mode
     if (MODE == MODE_PUSH_DEPOSIT) {
         cell_of<CONV, POW2>(P.map, xp, b0, xi);
         const double dphi = gather_dphi<K, REPG>(dsh, b0, xi);
@@ -259,7 +265,7 @@ k_vp_pass(double* __restrict__ x, double* __restrict__ v, const double* __restri
     if (MODE == MODE_PUSH_DEPOSIT) load_dcoef_ext<REPG>(dsh, dcoef, n, K - 2 > 0 ? K - 2 : 0);
     __syncthreads();
     if (!(MODE == MODE_PUSH_DEPOSIT && VM_PASS_EARLY_LOAD)) load(A, q);
-    if (MODE == MODE_DEPOSIT || (VM_AF_UNROLL && VAR == VAR_AF)) {
+    if (MODE == MODE_DEPOSIT || (VM_AF_UNROLL && VAR == VAR_AF) || (VM_PRIV_UNROLL && U == 1)) {
         // 16 B/particle pass, issue-bound: unrolled twice over the two buffer sets (no register moves)
         for (unsigned it = 0; it < iters; it += 2, q += 2 * chunk) {
             load(B, q + chunk);
@@ -337,21 +343,24 @@ inline size_t vm_af_core_doubles(int n, int order, int rep_log2)
 }
 inline bool plan_af(vm_ctx* ctx, int n, int order, int pass_mode, PassPlan* out)
 {
+    // Replicas first, the 16-fold gather table second: only 32 (one wavefront per atomic) and 16 replicas (two) pay --
+    // ncu, 1024 cells: 8 replicas cost 3.9 wavefronts per atomic, as many as a single grid -- and at 1024 cells 16 replicas
+    // with the plain table beat 8 replicas with the 16-fold one by 10 % (profiles/r02c_priv_variants_and_1024_replicas.jsonl).
     const size_t sm_total = 227 * 1024;
     int rl_max = 5;
     if (ctx->af_replicas > 0) { rl_max = 0; while ((1 << rl_max) < ctx->af_replicas) ++rl_max; }
-    for (int rg = 1; rg >= 0; --rg) {
-        if (rg && (pass_mode != MODE_PUSH_DEPOSIT || n <= 16 || ctx->no_repg)) continue;
-        for (int ctas = (ctx->af_ctas > 0 ? ctx->af_ctas : 1); ctas >= 1; --ctas) {    // (1 x 1024 measured >= 2 x 512 from 96 cells on, equal below)
-            const int threads = VM_AF_THREADS / ctas;
+    const int ctas = ctx->af_ctas > 0 ? ctx->af_ctas : 1;    // (1 x 1024 measured >= 2 x 512 from 96 cells on, equal below)
+    const int threads = VM_AF_THREADS / ctas;
+    if (threads < 128) return false;
+    for (int rl = rl_max; rl >= 0; --rl) {
+        for (int rg = 1; rg >= 0; --rg) {
+            if (rg && (pass_mode != MODE_PUSH_DEPOSIT || n <= 16 || ctx->no_repg)) continue;
             const size_t table = pass_mode == MODE_PUSH_DEPOSIT ? vm_gather_table_doubles(n, order, rg != 0) : 0;
-            for (int rl = rl_max; rl >= (rg ? 3 : 0); --rl) {        // (fewer than 8 replicas: rather give up the 16-fold table)
-                const size_t smem = (table + vm_af_core_doubles(n, order, rl) + (size_t)threads) * sizeof(double);
-                if (smem <= ctx->smem_optin && (size_t)ctas * (smem + 1024) <= sm_total && threads >= 128) {
-                    out->pl = DepositPlan{VAR_AF, rl, ctx->sm_count * ctas, threads, smem};
-                    out->repg = rg != 0;
-                    return true;
-                }
+            const size_t smem = (table + vm_af_core_doubles(n, order, rl) + (size_t)threads) * sizeof(double);
+            if (smem <= ctx->smem_optin && (size_t)ctas * (smem + 1024) <= sm_total) {
+                out->pl = DepositPlan{VAR_AF, rl, ctx->sm_count * ctas, threads, smem};
+                out->repg = rg != 0;
+                return true;
             }
         }
     }

@@ -228,13 +228,15 @@ bool want_bankq(vm_ctx* ctx, int n, int deposit_mode)
 }
 
 // Meshes from this size on run the limb-atomic fixed-point pass (VAR_AF, vm_deposit.cuh) in the default deposit mode.
-// Its cost does not depend on the mesh size (bound by the shared-memory data pipe: ~45 wavefronts per warp of particles);
-// the lane-private replicas below it are cheaper while enough warps fit next to them.  Measured crossover, interleaved A/B
-// on one box (profiles/r02b_af_ab.txt): fused step 40 cells 0.688 (lane-private) vs 0.677, 48 cells 0.649 vs 0.709; the
-// deposit-only pass (8-16 B/particle, the atomics are all of its work) only where no lane-private plan exists.
+// Its cost does not depend on the mesh size while 32 bank-steered replicas fit (up to 512 cells); the lane-private
+// per-warp replicas are only cheaper while two CTAs of 16 warps fit next to them.  Measured, interleaved A/B on one box
+// (profiles/r02c_af_variants2_thresholds.jsonl), fused step, fraction of the HBM roofline lane-private vs limb-atomic:
+// 16 cells 0.877 vs 0.861, 24 cells 0.803 vs 0.886, 32 cells 0.765 vs 0.878, 40 cells 0.708 vs 0.871.  The deposit-only
+// pass (8-16 B/particle: bound by instruction issue in this layout, by the shared-memory data pipe in the lane-private
+// one, 0.25-0.29 ms vs 0.23-0.26 ms per 1e8 particles) switches only where no lane-private plan exists.
 // Tuning key "af": 0 = this rule, 1 = always (n >= 8), -1 = never (the bank-sorted / round-1 layouts).
 #ifndef VM_AF_MIN_N
-#define VM_AF_MIN_N 44
+#define VM_AF_MIN_N 20
 #endif
 #define VM_AF_MIN_N_DEPOSIT 88
 bool want_af(vm_ctx* ctx, int n, int deposit_mode, int pass_mode)
