@@ -171,11 +171,12 @@ def test_pass_plans_of_the_benchmarked_meshes(vm):
     p = L.pass_plan(80, 4, 0)                             # deposit-only: lane-private while a plan exists (VM_AF_MIN_N_DEPOSIT = 88)
     assert (p.variant, p.grid, p.threads, p.pairs, p.max_threads) == (0, 148, 320, 4, 512)
     # limb atomics (variant 5) above: one full CTA per SM, 16-fold gather table, any mesh size (profiles/r02b_af_ab.txt)
-    for n in (20, 32, 64, 128, 256, 1024):
+    for n in (20, 32, 64, 128, 256, 512, 1024):
         p = L.pass_plan(n, 4, 1)
         assert (p.variant, p.grid, p.threads, p.pairs, p.max_threads) == (5, 148, 1024, 1, 1024), n
         # bank-steered replicas: conflict-free atomics (32 replicas) with the 16-fold gather table up to 512 cells; replicas go first
-        assert (p.replicas, p.gather_copies) == ((32, 16) if n <= 512 else (16, 1)), n
+        assert (p.replicas, p.gather_copies) == ((32, 16) if n <= 256 else ((32, 1) if n <= 512 else (16, 1))), n
+        assert p.smem_bytes <= 156 * 1024, n                      # (the rest of the 256 KB stays L1 for the streams)
     assert L.pass_plan(64, 4, 0).variant == 0 and L.pass_plan(128, 4, 0).variant == 5 and L.pass_plan(1024, 4, 0).variant == 5
     assert L.pass_plan(4096, 4, 1).variant == 5 and L.pass_plan(4096, 4, 1).gather_copies == 1     # 16 copies no longer fit
     assert L.pass_plan(16, 4, 0, 1).variant == 2          # VM_DEPOSIT_ATOMIC: the warp-aggregated A/B variant

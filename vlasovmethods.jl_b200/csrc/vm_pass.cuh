@@ -341,6 +341,9 @@ inline size_t vm_af_core_doubles(int n, int order, int rep_log2)
     const size_t limbs = (size_t)vm_af_pitch(n + order - 1, rep_log2) << rep_log2;
     return limbs > (size_t)(3 * n + 2) ? limbs : (size_t)(3 * n + 2);
 }
+#ifndef VM_AF_SMEM_CAP
+#define VM_AF_SMEM_CAP (156 * 1024)
+#endif
 inline bool plan_af(vm_ctx* ctx, int n, int order, int pass_mode, PassPlan* out)
 {
     // Replicas first, the 16-fold gather table second: only 32 (one wavefront per atomic) and 16 replicas (two) pay --
@@ -349,18 +352,24 @@ inline bool plan_af(vm_ctx* ctx, int n, int order, int pass_mode, PassPlan* out)
     const size_t sm_total = 227 * 1024;
     int rl_max = 5;
     if (ctx->af_replicas > 0) { rl_max = 0; while ((1 << rl_max) < ctx->af_replicas) ++rl_max; }
+    // Shared memory is carved out of the 256 KB L1: a 198 KB plan (512 cells, 32 replicas + 16-fold table) left too little
+    // L1 for the 64 KB of streaming loads the CTA keeps in flight and ran 10 % slower than either 140 KB alternative
+    // (profiles/r02c_af_smem_footprint_ab.jsonl), so plans stay below VM_AF_SMEM_CAP while one exists.
     const int ctas = ctx->af_ctas > 0 ? ctx->af_ctas : 1;    // (1 x 1024 measured >= 2 x 512 from 96 cells on, equal below)
     const int threads = VM_AF_THREADS / ctas;
     if (threads < 128) return false;
-    for (int rl = rl_max; rl >= 0; --rl) {
-        for (int rg = 1; rg >= 0; --rg) {
-            if (rg && (pass_mode != MODE_PUSH_DEPOSIT || n <= 16 || ctx->no_repg)) continue;
-            const size_t table = pass_mode == MODE_PUSH_DEPOSIT ? vm_gather_table_doubles(n, order, rg != 0) : 0;
-            const size_t smem = (table + vm_af_core_doubles(n, order, rl) + (size_t)threads) * sizeof(double);
-            if (smem <= ctx->smem_optin && (size_t)ctas * (smem + 1024) <= sm_total) {
-                out->pl = DepositPlan{VAR_AF, rl, ctx->sm_count * ctas, threads, smem};
-                out->repg = rg != 0;
-                return true;
+    for (int capped = 1; capped >= 0; --capped) {
+        for (int rl = rl_max; rl >= 0; --rl) {
+            for (int rg = 1; rg >= 0; --rg) {
+                if (rg && (pass_mode != MODE_PUSH_DEPOSIT || n <= 16 || ctx->no_repg)) continue;
+                const size_t table = pass_mode == MODE_PUSH_DEPOSIT ? vm_gather_table_doubles(n, order, rg != 0) : 0;
+                const size_t smem = (table + vm_af_core_doubles(n, order, rl) + (size_t)threads) * sizeof(double);
+                if (capped && (size_t)ctas * smem > VM_AF_SMEM_CAP) continue;
+                if (smem <= ctx->smem_optin && (size_t)ctas * (smem + 1024) <= sm_total) {
+                    out->pl = DepositPlan{VAR_AF, rl, ctx->sm_count * ctas, threads, smem};
+                    out->repg = rg != 0;
+                    return true;
+                }
             }
         }
     }
