@@ -552,8 +552,11 @@ def run_gpu(args):
             f2 = vm.DeviceField(ctx, 0.0, L_DOMAIN, ORDER, nh, 0)
             f2.run(p, DT, 3, 0, flags, 1.0)
             t = float(np.median([timed_region(f2, 10, 10, 11)[0] for _ in range(3)])) / 10
+            plan = vm._lib.pass_plan(nh, ORDER, 1)
+            layout = {0: "lane-private replicas", 4: "bank-sorted queues",
+                      5: "limb atomics, %d bank-steered replicas, %d-fold gather table" % (plan.replicas, plan.gather_copies)}.get(plan.variant, str(plan.variant))
             mesh[str(nh)] = {"ms_per_step": t, "particle_steps_per_s": ntot / t * 1e3,
-                             "step_hbm_frac": ALG_BYTES_PER_PARTICLE * nloc / t / 1e6 / peak}
+                             "step_hbm_frac": ALG_BYTES_PER_PARTICLE * nloc / t / 1e6 / peak, "deposit_layout": layout}
             f2.close()
         secondary = {"particles_total": ntot, "vspline": "41 knots, order 4, Dirichlet, v in (-10,10)",
                      "mesh_sweep_n_basis": mesh,
