@@ -219,6 +219,53 @@ def test_fixed_point_deposit_is_bitwise_independent_of_geometry(vm, oracle, rng,
     c.close()
 
 
+@pytest.mark.parametrize("n,k", [(20, 4), (33, 2), (64, 3), (64, 4), (200, 5), (256, 4), (512, 6), (1024, 4)])
+def test_limb_atomic_deposit_matches_oracle_and_is_order_independent(vm, oracle, rng, n, k):
+    """The default layout from 20 cells on: 64-bit fixed-point rows as two 32-bit limbs, native shared-
+    memory atomics with an exact carry, bank-steered replicas shared by the CTA.  Mixed-sign per-particle weights (the
+    two's-complement carry path), positions far outside the domain; against the oracle at 1e-12, and the SAME BITS for
+    every replica count / CTA shape, for the explicit VM_DEPOSIT_FIXED mode, and for the bank-sorted fixed-point layout."""
+    a, b = 0.0, 2 * math.pi / 0.3
+    npart = 200_001
+    x = rng.uniform(a - 3 * (b - a), b + 3 * (b - a), npart); v = rng.standard_normal(npart)
+    w = rng.standard_normal(npart) * (b - a) / npart                      # both signs
+    ref = oracle.deposit_periodic(x, w, a, b, n, k, 0)
+    scale = np.sum(np.abs(w)) / n                                         # (cancellation: compare against the mean |deposit|)
+    S = oracle.periodic_stiffness(a, b, n, k, 0)
+    xo, vo = x.copy(), v.copy()
+    oracle.integrate_vp(xo, vo, w, 0.1, 1.0, 4, 0, a, b, n, k, 0, S)
+    outs = []
+    tunings = [({}, 0), ({}, 2), ({"af_replicas": 1}, 0), ({"af_replicas": 8}, 0), ({"af_replicas": 16}, 0), ({"af_ctas": 2}, 0),
+               ({"af_ctas": 4}, 0), ({"no_repg": 1}, 0), ({"no_uniform_w": 1}, 0), ({"no_fuse": 1}, 0), ({"bankq": 1}, 2)]
+    for tune, mode in tunings:
+        c = vm.Context(0)
+        if n < 88 and "bankq" not in tune:
+            tune = dict(tune, af=1)          # below 88 cells the deposit-only CALL is lane-private by default (the fused step is not)
+        for key, val in tune.items():
+            c.set_tuning(key, val)
+        plan = vm._lib.pass_plan(n, k, 1)
+        assert plan.variant == 5                                          # (the default plan of this mesh: limb atomics)
+        fld = vm.DeviceField(c, a, b, k, n, 0)
+        p = vm.DeviceParticles(c, npart)
+        p.upload(x, v, w)
+        fld.deposit(p, mode)
+        rhs = fld.rhs
+        err = np.max(np.abs(rhs - ref)) / scale
+        assert err <= RTOL, (n, k, tune, mode, err)
+        p.upload(x, v, w)
+        fld.run(p, 0.1, 4, 0, vm._lib.VM_RUN_FIXED_DEPOSIT if mode == 2 else 0, 1.0)
+        xs, vs_, _ = p.download(w=False)
+        assert np.max(np.abs(xs - xo)) <= 1e-11 * (b - a) and np.max(np.abs(vs_ - vo)) <= 1e-11
+        if "no_fuse" in tune:            # separate fp64 reduce of converted CTA rows: equal to rounding only
+            assert relmax(rhs, np.frombuffer(outs[0][1])) <= 1e-13
+        else:
+            outs.append((tune, rhs.tobytes(), xs.tobytes(), vs_.tobytes()))
+        fld.close(); p.close(); c.close()
+    report(f"limb-atomic deposit n={n} k={k}", rhs=np.max(np.abs(np.frombuffer(outs[0][1]) - ref)) / scale)
+    for o in outs[1:]:
+        assert o[1:] == outs[0][1:], (n, k, o[0])
+
+
 def test_fixed_point_scale_edge_cases(vm, oracle, ctx):
     """One particle, huge / tiny / mixed-sign weights, zero weights: the scale keeps every contribution exact enough."""
     a, b, n, k = 0.0, 1.0, 16, 4
