@@ -16,6 +16,12 @@ __host__ __device__ inline int vm_af_pitch(int rows, int rep_log2)
     return rows + ((want - rows) & 31);
 }
 
+// most shared memory a limb-atomic plan takes while a smaller one exists: the rest of the 256 KB array is the L1 the
+// streaming loads are staged in (vm_pass.cuh: plan_af)
+#ifndef VM_AF_SMEM_CAP
+#define VM_AF_SMEM_CAP (156 * 1024)
+#endif
+
 enum { VAR_PRIV = 0, VAR_MATCH = 1, VAR_ATOMIC = 2, VAR_XOR = 3, VAR_AF = 5 };   // (4 is the bank-sorted pass in vm_pass_plan.variant)
 
 // ------------------------------------------------ order-independent sums -----

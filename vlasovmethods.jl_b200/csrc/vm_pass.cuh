@@ -94,12 +94,6 @@ inline size_t vm_gather_table_doubles(int n, int order, bool repg) { return (siz
 #ifndef VM_AF_PAIRS
 #define VM_AF_PAIRS 1           // pairs of particles in flight per thread in its fused / drift modes (A/B)
 #endif
-#ifndef VM_AF_L2PF
-#define VM_AF_L2PF 0            // 1: prefetch.global.L2 of the lines two iterations ahead (A/B)
-#endif
-#ifndef VM_AF_FORCE_UW
-#define VM_AF_FORCE_UW 0        // 1: BENCHMARK ONLY -- assume uniform weights at compile time (what a UW instantiation would gain)
-#endif
 // The canonical xi of the fixed-point layouts is (xi + 1) - 1.  (The bank-sorted pass clamps xi below 1 first because it
 // stores the mantissa of xi + 1; for the value computed here the clamp changes nothing: it only bites at xi == 1, where
 // both forms give 1.)
@@ -187,18 +181,11 @@ k_vp_pass(double* __restrict__ x, double* __restrict__ v, const double* __restri
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const unsigned q = q0 + u * stride;
-            if (!(VM_AF_FORCE_UW && VAR == VAR_AF)) buf[u].w = make_double2(0., 0.);            // out-of-range pairs deposit nothing
+            buf[u].w = make_double2(0., 0.);            // out-of-range pairs deposit nothing
             if (q < npairs) {
                 buf[u].x = ld_stream2(x + 2 * (size_t)q);
                 if (MODE != MODE_DEPOSIT) buf[u].v = ld_stream2(v + 2 * (size_t)q);
-                if (!(VM_AF_FORCE_UW && VAR == VAR_AF)) buf[u].w = P.uw ? make_double2(P.w0, P.w0) : ld_stream2(w + 2 * (size_t)q);
-                if (VM_AF_L2PF && VAR == VAR_AF && MODE != MODE_DEPOSIT) {
-                    const size_t qq = 2 * ((size_t)q + 2 * (size_t)chunk);
-                    if (qq < 2 * (size_t)npairs) {
-                        asm volatile("prefetch.global.L2 [%0];" ::"l"(x + qq));
-                        asm volatile("prefetch.global.L2 [%0];" ::"l"(v + qq));
-                    }
-                }
+                buf[u].w = P.uw ? make_double2(P.w0, P.w0) : ld_stream2(w + 2 * (size_t)q);
             }
         }
     };
@@ -241,7 +228,6 @@ k_vp_pass(double* __restrict__ x, double* __restrict__ v, const double* __restri
                     if (!active) continue;
                     active = true;
                 }
-                if (VM_AF_FORCE_UW && VAR == VAR_AF) buf[u].w = make_double2(P.w0, P.w0);
                 process<K, VAR, MODE, SPLIT, POW2, REPG, FIXED>(buf[u].x.x, buf[u].v.x, buf[u].w.x, active, P, dsh, wg, rep, lane);
                 process<K, VAR, MODE, SPLIT, POW2, REPG, FIXED>(buf[u].x.y, buf[u].v.y, buf[u].w.y, active, P, dsh, wg, rep, lane);
                 if (active && MODE != MODE_DEPOSIT) {
@@ -341,9 +327,6 @@ inline size_t vm_af_core_doubles(int n, int order, int rep_log2)
     const size_t limbs = (size_t)vm_af_pitch(n + order - 1, rep_log2) << rep_log2;
     return limbs > (size_t)(3 * n + 2) ? limbs : (size_t)(3 * n + 2);
 }
-#ifndef VM_AF_SMEM_CAP
-#define VM_AF_SMEM_CAP (156 * 1024)
-#endif
 inline bool plan_af(vm_ctx* ctx, int n, int order, int pass_mode, PassPlan* out)
 {
     // Replicas first, the 16-fold gather table second: only 32 (one wavefront per atomic) and 16 replicas (two) pay --
