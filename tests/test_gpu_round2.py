@@ -266,6 +266,52 @@ def test_limb_atomic_deposit_matches_oracle_and_is_order_independent(vm, oracle,
         assert o[1:] == outs[0][1:], (n, k, o[0])
 
 
+def test_limb_atomic_edge_cases(vm, oracle, rng):
+    """Limb-atomic layout at its edges: no particle, one particle on knots / domain ends / far outside, odd counts (the
+    tail particle), every particle in one cell (32-way same-address atomics), a mesh above the fused finish (per-CTA
+    conversion + separate reduce kernel), and short fused runs of 1 and 3 particles."""
+    a, b, k = 0.0, 1.0, 4
+    c = vm.Context(0)
+    c.set_tuning("af", 1)                       # also for the deposit-only call below 88 cells
+    for n in (24, 64, 2048):
+        fld = vm.DeviceField(c, a, b, k, n, 0)
+        p0 = vm.DeviceParticles(c, 0)
+        fld.deposit(p0, 0)
+        assert np.all(fld.rhs == 0), n
+        for xv in [0.0, 1.0, 0.5, 1.0 - 1e-17, -1e-17, 1.0 / n, 7.0, -7.0, 100.25]:
+            p1 = vm.DeviceParticles(c, 1)
+            p1.upload(np.array([xv]), np.array([0.0]), np.array([-2.5]))
+            fld.deposit(p1, 0)
+            ref = oracle.deposit_periodic(np.array([xv]), np.array([-2.5]), a, b, n, k, 0)
+            assert np.max(np.abs(fld.rhs - ref)) <= 1e-12 * 2.5, (n, xv)
+            p1.close()
+        for npart in (3, 65, 100_001):
+            x = rng.uniform(0.5, 0.5 + 1.0 / n, npart)                       # all in one cell
+            w = np.full(npart, 1.0 / npart)
+            p = vm.DeviceParticles(c, npart)
+            p.upload(x, np.zeros(npart), w)
+            fld.deposit(p, 0)
+            assert relmax(fld.rhs, oracle.deposit_periodic(x, w, a, b, n, k, 0)) <= RTOL, (n, npart)
+            p.close()
+        fld.close(); p0.close()
+    # fused runs with fewer particles than threads
+    n = 64
+    S = oracle.periodic_stiffness(a, b, n, k, 0)
+    fld = vm.DeviceField(c, a, b, k, n, 0)
+    for npart in (1, 3):
+        x = rng.uniform(a, b, npart); v = rng.standard_normal(npart); w = np.full(npart, (b - a) / npart)
+        p = vm.DeviceParticles(c, npart)
+        p.upload(x, v, w)
+        d = fld.run(p, 0.05, 6, 2, 0, 1.0)
+        xo, vo = x.copy(), v.copy()
+        dref = oracle.integrate_vp(xo, vo, w, 0.05, 1.0, 6, 2, a, b, n, k, 0, S)
+        xs, vs_, _ = p.download(w=False)
+        assert np.max(np.abs(xs - xo)) <= 1e-12 and np.max(np.abs(vs_ - vo)) <= 1e-12, npart
+        assert np.allclose(d[:, :3], dref, rtol=1e-10, atol=1e-13), npart
+        p.close()
+    fld.close(); c.close()
+
+
 def test_fixed_point_scale_edge_cases(vm, oracle, ctx):
     """One particle, huge / tiny / mixed-sign weights, zero weights: the scale keeps every contribution exact enough."""
     a, b, n, k = 0.0, 1.0, 16, 4
