@@ -74,7 +74,8 @@ int vm_ctx_device_info(vm_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor,
  *      "priv_min_warps" (0 = auto): fewest warps per SM for which the lane-private deposit is still chosen;
  *      "no_repg" (1: single field table in the fused pass instead of 16 bank-conflict-free copies);
  *      "af" (limb-atomic fixed-point pass, the default layout of larger meshes: 0 = auto -- fused step from 20 cells,
- *      deposit-only pass from 88 --, 1 = always, -1 = never), "af_ctas" (its CTAs per SM: 0 = auto, 1, 2, 4);
+ *      deposit-only pass from 88 --, 1 = always, -1 = never), "af_ctas" (its CTAs per SM: 0 = auto, 1, 2, 4),
+ *      "af_replicas" (its bank-steered replicas per CTA: 0 = as many as fit, else a power of two <= 32);
  *      "bankq" (bank-sorted pass, the layout "af" replaced: 0 = auto -- from 88 cells when af = -1 --, 1 = always, -1 = never);
  *      "force_match" (1: MATCH.ANY grouping instead of xor-shuffle rounds), "no_uniform_w" (1: always stream the
  *      weight array), "no_pdl" (1: no programmatic dependent launch), "no_fuse" (1: separate reduce / solve kernels);
@@ -197,7 +198,7 @@ int vm_deposit(vm_field* f, vm_particles* p, int mode);
 typedef struct vm_pass_plan {
     int variant;        /* 0 lane-private replicas, 1 MATCH.ANY grouping, 2 shared atomics, 3 xor-shuffle, 4 bank-sorted queues,
                            5 limb atomics (64-bit fixed point as two 32-bit words, native shared-memory adds with exact carry) */
-    int replicas;       /* replica grids per warp (per CTA for variant 2) */
+    int replicas;       /* replica grids per warp (per CTA for variants 2 and 5) */
     int grid, threads;  /* CTAs, threads per CTA */
     int pairs;          /* pairs of particles in flight per thread */
     int max_threads;    /* launch bound of the kernel instantiation (registers per thread = 65536 / max_threads) */
