@@ -591,6 +591,10 @@ def run_gpu(args):
             "cpu_baseline": cpu, "e2e": e2e, "parity": parity, "timing": timing, "ceilings": ceil,
             "gpu_launches": int(launches), "clocks": clocks,
             "step_hbm_frac": ALG_BYTES_PER_PARTICLE * nloc * args.steps / (ms * 1e-3) / 1e9 / peak,
+            # the same step against the copy kernel of tools/microbench/peaks timed IN THIS RUN (same box, same power /
+            # clock state: under the pool's sw_power_cap the copy kernel itself drops from ~6.5 to ~6.0 TB/s)
+            "step_frac_of_in_run_copy_rate": (ALG_BYTES_PER_PARTICLE * nloc * args.steps / (ms * 1e-3) / 1e9 / ceil["hbm_copy_gbs"]
+                                               if isinstance(ceil, dict) and ceil.get("hbm_copy_gbs") else None),
         }))
     if world > 1:
         dist.barrier()
