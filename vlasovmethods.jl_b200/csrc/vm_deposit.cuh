@@ -83,9 +83,9 @@ __device__ __forceinline__ void scatter(double* __restrict__ wg, int rep_log2, i
             for (int j = 0; j < K; ++j) {
                 // fix_of by limbs: the low word of the magic constant is zero, so the low limb is the low word of the
                 // fma itself and only the high word needs the subtraction
-                const double r = fma(val[j], fixscale, VM_FIX_MAGIC);
-                xl[j] = (unsigned)__double2loint(r);
-                xh[j] = (unsigned)__double2hiint(r) - 0x43380000u;
+                const double fx = fma(val[j], fixscale, VM_FIX_MAGIC);
+                xl[j] = (unsigned)__double2loint(fx);
+                xh[j] = (unsigned)__double2hiint(fx) - 0x43380000u;
             }
 #pragma unroll
             for (int j = 0; j < K; ++j)          // the K returning atomics in flight together
