@@ -264,6 +264,18 @@ def test_limb_atomic_deposit_matches_oracle_and_is_order_independent(vm, oracle,
     report(f"limb-atomic deposit n={n} k={k}", rhs=np.max(np.abs(np.frombuffer(outs[0][1]) - ref)) / scale)
     for o in outs[1:]:
         assert o[1:] == outs[0][1:], (n, k, o[0])
+    # the fp64-accumulating layouts it replaced stay selectable (tuning af = -1: lane-private tiers / bank-sorted queues)
+    c = vm.Context(0)
+    c.set_tuning("af", -1)
+    fld = vm.DeviceField(c, a, b, k, n, 0)
+    p = vm.DeviceParticles(c, npart)
+    p.upload(x, v, w)
+    fld.deposit(p, 0)
+    assert np.max(np.abs(fld.rhs - ref)) / scale <= RTOL, (n, k, "af=-1")
+    fld.run(p, 0.1, 4, 0, 0, 1.0)
+    xs, vs_, _ = p.download(w=False)
+    assert np.max(np.abs(xs - xo)) <= 1e-11 * (b - a) and np.max(np.abs(vs_ - vo)) <= 1e-11
+    fld.close(); p.close(); c.close()
 
 
 def test_limb_atomic_edge_cases(vm, oracle, rng):
