@@ -151,7 +151,13 @@ typedef enum vm_fill_kind {
     VM_FILL_UNIFORM = 3,         /* uniform.jl:10-33   params: xlo, xhi, vlo, vhi           */
     VM_FILL_SHIFTED_NORMAL_V = 4,/* shiftednormalv.jl  params: xlo, xhi, shift              */
     VM_FILL_SHIFTED_UNIFORM = 5, /* shifteduniform.jl  params: xlo, xhi, vlo, vhi, shift    */
-    VM_FILL_LANDAU = 6           /* (1+eps cos kx) Maxwellian  params: eps, kappa           */
+    VM_FILL_LANDAU = 6,          /* (1+eps cos kx) Maxwellian  params: eps, kappa           */
+    VM_FILL_BUMP_ON_TAIL_SOBOL = 7,    /* bumpontail.jl:43-75 as written: proposals from a 2-D Sobol sequence (Gray-code
+                                          order, `skip` points skipped), accept-reject in x against f_x / (1 + eps),
+                                          inverse CDF in v, w = L/N.  params: eps, kappa, alpha, sigma, v0, skip
+                                          (skip < 0: Sobol.jl's skip(s, 2N) = the largest power of two <= 2N + 1) */
+    VM_FILL_BUMP_ON_TAIL_SOBOL_IS = 8  /* bumpontail.jl:90-121 (ImportanceSampling): every Sobol proposal kept,
+                                          w = f_x(x) L/N.  params as kind 7 */
 } vm_fill_kind;
 int vm_particles_fill(vm_particles* p, int kind, const double* params, int nparams,
                       unsigned long long seed, long first_index, long total_n);

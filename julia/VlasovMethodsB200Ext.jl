@@ -43,6 +43,23 @@ end
 mark_host_dirty!(dist::ParticleDistribution) = haskey(PARTICLES, dist) && (PARTICLES[dist][2][] = false)
 tohost!(dist::ParticleDistribution) = (B.download!(hostmatrix(dist), device(dist)); dist)
 
+# ----------------------------------------------------------------------------------------------- initial loads --
+# src/examples/bumpontail.jl:33-75, 90-121: draw!(dist, f_x, params, sampling) on the device.  Fill kinds 7 / 8 of
+# vm_particles_fill are the reference's own procedure (2-D Sobol proposals in sequence order, accept-reject in x or
+# importance weights, inverse CDF in v); its `rand` calls are Julia's unseeded global RNG there, Philox keyed by
+# (seed, proposal index) here.  The host matrix is refreshed so that dist.particles stays the state of record.
+function VlasovMethods.draw!(dist::ParticleDistribution{1,1}, fₓ::Base.Callable, params::VlasovMethods.BumpOnTail,
+                             sampling::Union{VlasovMethods.AcceptRejectSampling, VlasovMethods.ImportanceSampling}; seed = 20240601)
+    dev, cur = get!(PARTICLES, dist) do
+        (B.DeviceParticles(length(dist.particles)), Ref(false))
+    end
+    kind = sampling isa VlasovMethods.ImportanceSampling ? 8 : 7
+    B.fill!(dev, kind, Float64[params.ε, params.κ, params.α, params.σ, params.v₀, -1.0]; seed = seed)
+    cur[] = true
+    tohost!(dist)
+    return dist
+end
+
 function device(potential::Potential{<:PeriodicBSplineBasis})
     get!(FIELDS, potential) do
         basis = potential.basis

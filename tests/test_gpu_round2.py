@@ -565,3 +565,62 @@ def test_run_diagnostics_cadence_across_chunks(vm, ctx):
     with pytest.raises(ValueError):
         vm.run_(integ, None, save_every=3, diag_every=2)
     vm.set_default_context(None)
+
+
+# ------------------------------------------------------------- Sobol loads ---
+def test_sobol_bump_on_tail_loads(vm, ctx):
+    """draw!(dist, f_x, ::BumpOnTail, ::ImportanceSampling / ::AcceptRejectSampling) (bumpontail.jl:90-121, 43-75) on the
+    device: proposals are the points of the unscrambled 2-D Sobol sequence in Gray-code order (checked against scipy's
+    generator, point for point), kept in order; accept-reject thins them against f_x / (1 + eps)."""
+    from scipy.stats import qmc
+    from scipy.special import ndtri
+    eps, kappa, alpha, sigma, v0 = 0.03, 0.3, 0.1, 0.5, 4.5
+    L = 2 * math.pi / kappa
+    n = 300_001
+    skip = 1
+    while 2 * skip <= 2 * n + 1:
+        skip *= 2                                   # Sobol.jl: skip(s, 2N) skips the largest power of two <= 2N + 1
+    nprop = int(n * (1 + eps) * 1.02) + 65536
+    sob = qmc.Sobol(2, scramble=False, bits=32)
+    sob.fast_forward(skip + 1)                      # (scipy's point 0 is the origin, which Sobol.jl leaves out)
+    y = sob.random(nprop)
+    p = vm.DeviceParticles(ctx, n)
+    # importance sampling: particle i IS proposal i
+    p.fill(vm._lib.VM_FILL_BUMP_ON_TAIL_SOBOL_IS, [eps, kappa, alpha, sigma, v0, -1.0], 7)
+    x, v, w = p.download()
+    assert np.max(np.abs(x - y[:n, 0] * L)) <= 1e-12 * L
+    assert np.max(np.abs(w - (1 - eps * np.cos(kappa * x)) * L / n)) <= 1e-15
+    bulk = ndtri(y[:n, 1])
+    is_bulk = np.abs(v - bulk) <= 1e-9 * (1 + np.abs(bulk))
+    is_tail = np.abs(v - (bulk * sigma + v0)) <= 1e-9 * (1 + np.abs(bulk))
+    assert np.all(is_bulk | is_tail) and abs(is_tail.mean() - alpha) < 5e-3
+    assert abs(w.sum() - L) < 2e-4 * L                                   # f_x integrates to L (quasi-Monte-Carlo error)
+    # accept-reject: an ordered subsequence of the same proposals, density 1 - eps cos(kappa x), w = L / N
+    p.fill(vm._lib.VM_FILL_BUMP_ON_TAIL_SOBOL, [eps, kappa, alpha, sigma, v0, -1.0], 7)
+    xa, va, wa = p.download()
+    assert np.all(wa == L / n)
+    prop = y[:, 0] * L
+    order = np.argsort(prop, kind="stable")
+    where = np.searchsorted(prop[order], xa)
+    where = np.clip(where, 0, nprop - 1)
+    cand = order[where]
+    assert np.max(np.abs(prop[cand] - xa)) <= 1e-12 * L                  # every particle is one of the proposals ...
+    assert np.all(np.diff(cand) > 0)                                     # ... taken in sequence order
+    assert abs(n / (cand[-1] + 1) - 1 / (1 + eps)) < 5e-3                # acceptance rate 1 / (1 + eps)
+    assert abs(np.mean(np.cos(kappa * xa)) - (-eps / 2)) < 2e-3
+    assert abs((va > 3.0).mean() - alpha) < 5e-3
+    # sharding independence: two half shards == one full load
+    q = vm.DeviceParticles(ctx, n // 2)
+    q.fill(vm._lib.VM_FILL_BUMP_ON_TAIL_SOBOL, [eps, kappa, alpha, sigma, v0, -1.0], 7, 0, n)
+    x1, v1, _ = q.download()
+    q2 = vm.DeviceParticles(ctx, n - n // 2)
+    q2.fill(vm._lib.VM_FILL_BUMP_ON_TAIL_SOBOL, [eps, kappa, alpha, sigma, v0, -1.0], 7, n // 2, n)
+    x2, v2, _ = q2.download()
+    assert np.array_equal(np.concatenate([x1, x2]), xa) and np.array_equal(np.concatenate([v1, v2]), va)
+    # the mirror: initialize!(dist, BumpOnTail()) defaults to AcceptRejectSampling (bumpontail.jl:33-35)
+    vm.set_default_context(ctx)
+    dist = vm.initialize_(vm.ParticleDistribution(1, 1, 20_000), vm.BumpOnTail(), seed=7)
+    d2 = vm.initialize_(vm.ParticleDistribution(1, 1, 20_000), vm.BumpOnTail(), vm.ImportanceSampling(), seed=7)
+    assert np.all(dist.particles.w == L / 20_000) and d2.particles.w.std() > 0
+    vm.set_default_context(None)
+    p.close(); q.close(); q2.close()

@@ -94,7 +94,8 @@ VM_DEPOSIT_DETERMINISTIC, VM_DEPOSIT_ATOMIC, VM_DEPOSIT_FIXED = 0, 1, 2
 VM_RUN_SPLIT_KICK, VM_RUN_FROZEN_FIELD, VM_RUN_ATOMIC_DEPOSIT, VM_RUN_UNFUSED, VM_RUN_FIXED_DEPOSIT = 1, 2, 4, 8, 16
 VM_VF_KEEP_POTENTIAL = 1
 (VM_FILL_NORMAL, VM_FILL_BUMP_ON_TAIL, VM_FILL_DOUBLE_MAXWELLIAN, VM_FILL_UNIFORM,
- VM_FILL_SHIFTED_NORMAL_V, VM_FILL_SHIFTED_UNIFORM, VM_FILL_LANDAU) = range(7)
+ VM_FILL_SHIFTED_NORMAL_V, VM_FILL_SHIFTED_UNIFORM, VM_FILL_LANDAU, VM_FILL_BUMP_ON_TAIL_SOBOL,
+ VM_FILL_BUMP_ON_TAIL_SOBOL_IS) = range(9)
 VM_OK, VM_ERR_INVALID, VM_ERR_CUDA, VM_ERR_NOMEM, VM_ERR_NCCL, VM_ERR_UNSUPPORTED, VM_ERR_NO_DEVICE = range(7)   # vm_status
 
 _lib = None

@@ -175,6 +175,12 @@ def initialize_(dist: ParticleDistribution, params, sampling: SamplingMethod = N
     The reference samples from Julia's unseeded global RNG; here the same distributions are
     generated on the device by a counter-based generator keyed by (seed, global particle index)."""
     kind, p = _fill_args(params)
+    if isinstance(params, BumpOnTail) and not isinstance(sampling, NoSampling):
+        # draw!(dist, f_x, params, ::AcceptRejectSampling) -- the default of initialize!(dist, ::BumpOnTail) -- and
+        # ::ImportanceSampling (bumpontail.jl:43-75, 90-121): Sobol proposals as in the reference; NoSampling() selects the
+        # inverse-CDF load of the same density (what bench.py fills with)
+        kind = L.VM_FILL_BUMP_ON_TAIL_SOBOL_IS if isinstance(sampling, ImportanceSampling) else L.VM_FILL_BUMP_ON_TAIL_SOBOL
+        p = list(p) + [-1.0]
     if dist._dev is None:
         dist._dev = DeviceParticles(dist.ctx or default_context(), len(dist.particles))
     dist._dev.fill(kind, p, seed, dist.first_index, dist.total)
