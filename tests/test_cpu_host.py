@@ -247,3 +247,29 @@ def test_header_is_plain_c_and_links_from_c(vm, tmp_path):
     else:
         r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=60)
         assert r.returncode == 3 and "no CPU path" in r.stderr, (r.returncode, r.stderr)
+
+
+def test_sobol_direction_numbers_of_the_device_load():
+    """The 2-D Sobol construction vm_fill.cu uses for the bump-on-tail draws (fill kinds 7 / 8), restated in Python: point k =
+    XOR over the set bits b of gray(k) of V_b, dimension 1 V_b = 2^(31-b), dimension 2 m_0 = 1, m_b = 2 m_(b-1) ^ m_(b-1),
+    V_b = m_b 2^(31-b) (Joe-Kuo, primitive polynomial x + 1).  Must be scipy's unscrambled generator point for point (the
+    GPU test compares the device output with the same generator)."""
+    from scipy.stats import qmc
+
+    def sobol2(k):
+        g = k ^ (k >> 1)
+        x2, m, b = 0, 1, 0
+        while g >> b:
+            if (g >> b) & 1:
+                x2 ^= (m << (31 - b)) & 0xFFFFFFFF
+            m = (m ^ (m << 1)) & 0xFFFFFFFF
+            b += 1
+        x1 = int(format(g, "032b")[::-1], 2)
+        return x1 / 2.0**32, x2 / 2.0**32
+
+    ref = qmc.Sobol(2, scramble=False, bits=32).random(1 << 12)
+    mine = np.array([sobol2(k) for k in range(1 << 12)])
+    assert np.array_equal(mine, ref)
+    sob = qmc.Sobol(2, scramble=False, bits=32)
+    sob.fast_forward((1 << 20) + 1)
+    assert np.array_equal(np.array([sobol2((1 << 20) + 1 + j) for j in range(64)]), sob.random(64))
