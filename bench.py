@@ -27,6 +27,9 @@ A "step" = one Strang step: E gather -> kick -> drift -> charge deposition -> al
 `value`    : median over `repeats` timed regions of K steps each (min / max alongside); before every region the ranks
            are aligned on the device by one untimed fused step (its in-kernel exchange waits for the slowest rank).
 `ceilings` : tools/microbench/peaks (fp64 FMA rate, shared-memory wavefront rate, copy bandwidth) run on the same GPU.
+`step_frac_of_in_run_copy_rate`: the step against that copy kernel -- same box, same power / clock state (`roofline.frac`
+           and `step_hbm_frac` use the driver's cool-GPU peak of MEASURED_PEAKS.json, as the contract asks).
+`secondary.mesh_sweep_n_basis[*].deposit_layout`: which deposition layout the planner chose for that mesh.
 """
 from __future__ import annotations
 
