@@ -78,7 +78,9 @@ int vm_ctx_device_info(vm_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor,
  *      "af_replicas" (its bank-steered replicas per CTA: 0 = as many as fit, else a power of two <= 32);
  *      "bankq" (bank-sorted pass, the layout "af" replaced: 0 = auto -- from 88 cells when af = -1 --, 1 = always, -1 = never);
  *      "force_match" (1: MATCH.ANY grouping instead of xor-shuffle rounds), "no_uniform_w" (1: always stream the
- *      weight array), "no_pdl" (1: no programmatic dependent launch), "no_fuse" (1: separate reduce / solve kernels);
+ *      weight array), "no_pdl" (1: no programmatic dependent launch), "no_fuse" (1: separate reduce / solve kernels),
+ *      "no_presolve" (1: meshes above 128 cells launch the solve kernel between fused passes instead of solving in the
+ *      next pass's prologue);
  *      "profile" (see vm_profile_read). */
 int vm_ctx_set_tuning(vm_ctx* ctx, const char* key, int value);
 

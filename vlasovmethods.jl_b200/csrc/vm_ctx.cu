@@ -290,6 +290,7 @@ int vm_ctx_set_tuning(vm_ctx* ctx, const char* key, int value)
     }
     else if (k == "bankq") { VM_REQUIRE(value >= -1 && value <= 1, "bankq must be -1, 0 or 1"); ctx->bankq = value; }
     else if (k == "af") { VM_REQUIRE(value >= -1 && value <= 1, "af must be -1, 0 or 1"); ctx->af = value; }
+    else if (k == "no_presolve") ctx->no_presolve = value;   // 1: separate solve kernel between the fused passes of large meshes (A/B)
     else if (k == "af_replicas") {
         VM_REQUIRE(value == 0 || (value >= 1 && value <= 32 && (value & (value - 1)) == 0), "af_replicas must be a power of two <= 32");
         ctx->af_replicas = value;

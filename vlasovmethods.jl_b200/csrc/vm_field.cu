@@ -32,59 +32,15 @@ __global__ void __launch_bounds__(256) k_reduce_rows(const double* __restrict__ 
     }
 }
 
-// phi = G (*) (rhs - mean(rhs))  (circular convolution with the pseudo-inverse kernel G), and
-// dcoef_m = (phi_{m+1} - phi_m) / h, the coefficients of the derivative spline (E = -phi').
-// Each lane accumulates phi_i and phi_{i+1} with the same chunking over j, so the phi_{i+1} it uses
-// is bit-identical to the phi_{i+1} its neighbour stores: dcoef is a pure function of the stored
-// phi (same bits as k_dcoef_from_phi), as the reference's ExternalField/PoissonField test demands.
-// Every CTA recomputes the mean in the same fixed order, so all CTAs (and all ranks) agree bitwise.
+// The Poisson solve as a kernel of its own: one tile of 32 outputs per CTA (poisson_solve_tile, vm_internal.cuh).
 __global__ void __launch_bounds__(256) k_poisson_solve(const double* __restrict__ rhs, const double* __restrict__ G,
                                                        int n, double inv_h,
                                                        double* __restrict__ phi, double* __restrict__ dcoef)
 {
     extern __shared__ double r[];          // n
-    __shared__ double red[2][8][33];
+    __shared__ double red[2 * 8 * 33];
     __shared__ double wsum[8];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double s = 0.0;
-    for (int j = threadIdx.x; j < n; j += 256) s += rhs[j];
-    s = warp_sum(s);
-    if (lane == 0) wsum[warp] = s;
-    __syncthreads();
-    double mean = 0.0;
-#pragma unroll
-    for (int q = 0; q < 8; ++q) mean += wsum[q];
-    mean /= (double)n;
-    for (int j = threadIdx.x; j < n; j += 256) r[j] = rhs[j] - mean;
-    __syncthreads();
-
-    const int i = blockIdx.x * 32 + lane;
-    const int len = (n + 7) / 8;
-    const int j0 = warp * len, j1 = min(n, j0 + len);
-    double a0 = 0.0, a1 = 0.0;             // partial sums of phi_i and phi_{i+1}
-    if (i < n) {
-        int idx = i - j0;
-        if (idx < 0) idx += n;
-        double g1 = __ldg(G + (idx + 1 == n ? 0 : idx + 1));
-        for (int j = j0; j < j1; ++j) {
-            const double rj = r[j];
-            const double g0 = __ldg(G + idx);
-            a0 = fma(g0, rj, a0);
-            a1 = fma(g1, rj, a1);
-            g1 = g0;
-            idx = (idx == 0) ? n - 1 : idx - 1;
-        }
-    }
-    red[0][warp][lane] = a0;
-    red[1][warp][lane] = a1;
-    __syncthreads();
-    if (warp == 0 && i < n) {
-        double p0 = 0.0, p1 = 0.0;
-#pragma unroll
-        for (int q = 0; q < 8; ++q) { p0 += red[0][q][lane]; p1 += red[1][q][lane]; }
-        phi[i] = p0;
-        dcoef[i] = (p1 - p0) * inv_h;
-    }
+    poisson_solve_tile(blockIdx.x, rhs, G, n, inv_h, phi, dcoef, r, red, wsum);
 }
 
 // dcoef_m = (phi_{m+1} - phi_m) / h for externally prescribed coefficients (ExternalField)
@@ -186,6 +142,7 @@ void vm_field_reduce_rows(vm_field* f, const double* rows, int nrows, int ncols,
 void vm_field_solve_local(vm_field* f, bool allreduce)
 {
     vm_ctx* ctx = f->ctx;
+    f->solve_pending = false;
     // rhs may already hold the sum over the ranks (fused peer exchange, an earlier solve, vm_vp_run): reducing it
     // again would scale phi by nranks -- update!(potential) of the reference can be repeated safely, so can this
     if (allreduce && ctx->nranks > 1 && !f->rhs_global) {
@@ -312,6 +269,8 @@ int vm_field_create(vm_ctx* ctx, double a, double b, int order, int n_basis, int
         VM_CUDA(cudaMalloc(&f->dcoef, nb));
         VM_CUDA(cudaMalloc(&f->G, nb));
         VM_CUDA(cudaMalloc(&f->stencil_s, k * sizeof(double)));
+        VM_CUDA(cudaMalloc(&f->solve_count, 2 * sizeof(unsigned)));          // [0] tiles solved, [1] wait timed out
+        VM_CUDA(cudaMemsetAsync(f->solve_count, 0, 2 * sizeof(unsigned), ctx->stream));
         VM_CUDA(cudaMemsetAsync(f->rhs, 0, nb + (VM_DIAG_COLS + 4) * sizeof(double), ctx->stream));
         VM_CUDA(cudaMemsetAsync(f->phi, 0, nb, ctx->stream));
         VM_CUDA(cudaMemsetAsync(f->dcoef, 0, nb, ctx->stream));
@@ -330,15 +289,24 @@ int vm_field_destroy(vm_field* f)
     if (!f) return VM_OK;
     vm_child_quiesce(f->ctx, f->device);
     cudaFree(f->rhs); cudaFree(f->phi); cudaFree(f->dcoef); cudaFree(f->G);
-    cudaFree(f->stencil_s); cudaFree(f->diag); cudaFree(f->ext_phi); cudaFree(f->ext_dcoef);
+    cudaFree(f->stencil_s); cudaFree(f->diag); cudaFree(f->ext_phi); cudaFree(f->ext_dcoef); cudaFree(f->solve_count);
     delete f;
     return VM_OK;
+}
+
+// after a stream sync: a fused pass that gave up waiting for the in-pass solve (pass_presolve) left a flag
+void vm_field_check_solve_error(vm_field* f)
+{
+    unsigned e = 0;
+    VM_CUDA(cudaMemcpy(&e, f->solve_count + 1, sizeof(e), cudaMemcpyDeviceToHost));
+    if (e) throw vm_error(VM_ERR_CUDA, "in-pass Poisson solve timed out (not all CTAs of the fused pass resident?); set tuning no_presolve = 1");
 }
 
 static void get_vec(vm_field* f, const double* dev, double* host)
 {
     VM_CUDA(cudaMemcpyAsync(host, dev, (size_t)f->n * sizeof(double), cudaMemcpyDeviceToHost, f->ctx->stream));
     VM_CUDA(cudaStreamSynchronize(f->ctx->stream));
+    vm_field_check_solve_error(f);
 }
 
 int vm_field_get_rhs(vm_field* f, double* host)

@@ -57,6 +57,7 @@ struct vm_ctx {
     // tuning (0 = auto)
     int ctas_per_sm = 0, threads_per_cta = 0, replicas = 0, profile = 0, no_fuse = 0, no_pdl = 0, force_match = 0, no_uniform_w = 0;
     int bankq = 0;      // bank-sorted large-mesh pass: 0 = auto (n >= 256), 1 = always, -1 = never
+    int no_presolve = 0;       // 1: meshes above 128 cells keep the separate k_poisson_solve launch between fused passes (A/B)
     int af_replicas = 0;       // bank-steered replicas per CTA of the limb-atomic pass (0 = as many as fit, <= 32)
     int af = 0, af_ctas = 0;   // limb-atomic fixed-point pass: 0 = auto (from VM_AF_MIN_N cells), 1 = always, -1 = never; CTAs per SM (0 = auto)
     int pairs = 0, priv_min_warps = 0, no_repg = 0;   // pairs in flight per thread / fewest warps the lane-private deposit accepts
@@ -121,6 +122,11 @@ struct vm_field {
     CellMap map{};
     double *rhs = nullptr, *phi = nullptr, *dcoef = nullptr;  // device, n each
     bool rhs_global = true;                                   // rhs holds the sum over all ranks (false: this rank's deposit only)
+    // meshes above 128 cells inside vm_vp_run: the solve of a deposit is done by the first CTAs of the NEXT fused pass
+    // (vm_pass.cuh: pass_presolve) instead of a kernel of its own; true while rhs is newer than phi / dcoef
+    bool solve_pending = false;
+    unsigned* solve_count = nullptr;                          // device: tiles solved so far (monotonic)
+    unsigned solve_target = 0;                                // host mirror: value of *solve_count after the last presolve
     double *ext_phi = nullptr, *ext_dcoef = nullptr;          // device: coefficient history of vm_vp_run_external (n x ext_cols)
     int ext_cols = 0;
     double *G = nullptr;                                      // device: circulant pseudo-inverse kernel (first column)
@@ -334,5 +340,66 @@ __device__ __forceinline__ double warp_sum(double v)
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(VM_FULL_MASK, v, o);
     return v;
 }
+
+// phi = G (*) (rhs - mean(rhs))  (circular convolution with the pseudo-inverse kernel G), and
+// dcoef_m = (phi_{m+1} - phi_m) / h, the coefficients of the derivative spline (E = -phi'): 32 outputs (one tile) by the
+// first 256 threads of the calling CTA; ALL threads of the CTA must call (it synchronises the CTA).
+// Each lane accumulates phi_i and phi_{i+1} with the same chunking over j, so the phi_{i+1} it uses
+// is bit-identical to the phi_{i+1} its neighbour stores: dcoef is a pure function of the stored
+// phi (same bits as k_dcoef_from_phi), as the reference's ExternalField/PoissonField test demands.
+// Every tile recomputes the mean in the same fixed order, so all tiles (and all ranks) agree bitwise.
+// r: n doubles, red: 2 * 8 * 33 doubles, wsum: 8 doubles of shared memory.  rhs is read with ld.cg (it may have been
+// written by another SM's last CTA in the kernel before this one, or exchanged over NVLink).
+__device__ __forceinline__ void poisson_solve_tile(int tile, const double* __restrict__ rhs, const double* __restrict__ G,
+                                                   int n, double inv_h, double* __restrict__ phi, double* __restrict__ dcoef,
+                                                   double* __restrict__ r, double* __restrict__ red, double* __restrict__ wsum)
+{
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const bool work = t < 256;
+    if (work) {
+        double s = 0.0;
+        for (int j = t; j < n; j += 256) s += __ldcg(rhs + j);
+        s = warp_sum(s);
+        if (lane == 0) wsum[warp] = s;
+    }
+    __syncthreads();
+    double mean = 0.0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) mean += wsum[q];
+    mean /= (double)n;
+    if (work)
+        for (int j = t; j < n; j += 256) r[j] = __ldcg(rhs + j) - mean;
+    __syncthreads();
+    const int i = tile * 32 + lane;
+    if (work) {
+        const int len = (n + 7) / 8;
+        const int j0 = warp * len, j1 = min(n, j0 + len);
+        double a0 = 0.0, a1 = 0.0;             // partial sums of phi_i and phi_{i+1}
+        if (i < n) {
+            int idx = i - j0;
+            if (idx < 0) idx += n;
+            double g1 = __ldg(G + (idx + 1 == n ? 0 : idx + 1));
+            for (int j = j0; j < j1; ++j) {
+                const double rj = r[j];
+                const double g0 = __ldg(G + idx);
+                a0 = fma(g0, rj, a0);
+                a1 = fma(g1, rj, a1);
+                g1 = g0;
+                idx = (idx == 0) ? n - 1 : idx - 1;
+            }
+        }
+        red[(0 * 8 + warp) * 33 + lane] = a0;
+        red[(1 * 8 + warp) * 33 + lane] = a1;
+    }
+    __syncthreads();
+    if (warp == 0 && i < n) {
+        double p0 = 0.0, p1 = 0.0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { p0 += red[(0 * 8 + q) * 33 + lane]; p1 += red[(1 * 8 + q) * 33 + lane]; }
+        phi[i] = p0;
+        dcoef[i] = (p1 - p0) * inv_h;
+    }
+}
+#define VM_SOLVE_SCRATCH_DOUBLES(n) ((n) + 2 * 8 * 33 + 8)      // r + red + wsum
 
 #endif  // __CUDACC__

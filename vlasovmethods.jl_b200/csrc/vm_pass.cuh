@@ -25,6 +25,14 @@ struct PassParams {
     int repg;                 // fused pass: the gather table is stored VM_GATHER_COPIES times (conflict-free reads)
     double w0;
     double fixscale;          // VM_DEPOSIT_FIXED: 2^S (contributions are accumulated as 64-bit integers); 0: fp64 accumulation
+    // presolve (fused limb-atomic pass on meshes above 128 cells): the Poisson solve of the PREVIOUS pass's deposit is
+    // done by the first ps_tiles CTAs of this grid before the particle loop (0: dcoef is already current)
+    int ps_tiles;
+    unsigned ps_target;       // value of *ps_count once every tile is done
+    unsigned* ps_count;
+    unsigned* ps_err;
+    const double *ps_rhs, *ps_G;
+    double *ps_phi, *ps_dcoef;
 };
 
 // ---------------------------------------------------------------- gather ----
@@ -138,6 +146,33 @@ __device__ __forceinline__ void process(double& xp, double& vp, double wp, bool 
     scatter<K, VAR, FIXED>(wg, P.rep_log2, rep, lane, b0, val, active, P.fixscale);
 }
 
+// The solve between two fused passes without a kernel of its own (meshes above 128 cells; up to 128 the last CTA of the
+// depositing pass solves).  All CTAs of this grid are resident (one per SM), so the first ps_tiles of them each solve one
+// tile of 32 outputs -- the arithmetic of k_poisson_solve, same bits -- publish phi / dcoef, and bump a counter that every
+// CTA waits for before it loads its gather table (with ld.cg: the table was written during this kernel).  scr: shared
+// memory scratch of VM_SOLVE_SCRATCH_DOUBLES(n) doubles, zero on entry and zeroed again on exit (the replica grids).
+// Removes two launch boundaries per step: 14.4 -> see profiles/r02c_fixed_cost_per_step.jsonl.
+__device__ __forceinline__ void pass_presolve(const PassParams& P, double* __restrict__ scr)
+{
+    const int n = P.map.n;
+    if ((int)blockIdx.x < P.ps_tiles) {
+        poisson_solve_tile((int)blockIdx.x, P.ps_rhs, P.ps_G, n, P.map.inv_h, P.ps_phi, P.ps_dcoef, scr, scr + n, scr + n + 2 * 8 * 33);
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) atomicAdd(P.ps_count, 1u);
+        for (int i = threadIdx.x; i < VM_SOLVE_SCRATCH_DOUBLES(n); i += blockDim.x) scr[i] = 0.0;
+    }
+    if (threadIdx.x == 0) {
+        const long long t0 = clock64();
+        unsigned c;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(c) : "l"(P.ps_count) : "memory");
+            if ((int)(c - P.ps_target) < 0 && clock64() - t0 > (1ll << 33)) { atomicExch(P.ps_err, 1u); break; }   // ~4 s: give up, host reports
+        } while ((int)(c - P.ps_target) < 0);
+    }
+    __syncthreads();
+}
+
 template <int MODE>
 struct PairBuf {
     double2 x, v, w;
@@ -248,7 +283,19 @@ k_vp_pass(double* __restrict__ x, double* __restrict__ v, const double* __restri
     // completion first).  What the finish of the previous kernel writes (dcoef) is read after griddepcontrol.wait.
     if (MODE == MODE_PUSH_DEPOSIT && VM_PASS_EARLY_LOAD) load(A, q);
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    if (MODE == MODE_PUSH_DEPOSIT) load_dcoef_ext<REPG>(dsh, dcoef, n, K - 2 > 0 ? K - 2 : 0);
+    if (MODE == MODE_PUSH_DEPOSIT) {
+        if (VAR == VAR_AF && P.ps_tiles > 0) {
+            __syncthreads();                                  // (the zero-fill of the grids, which double as scratch here)
+            pass_presolve(P, grid);
+            constexpr int ext = K - 2 > 0 ? K - 2 : 0, copies = REPG ? VM_GATHER_COPIES : 1;
+            for (int i = threadIdx.x; i < (n + ext) * copies; i += blockDim.x) {
+                const int m = i / copies;
+                dsh[i] = __ldcg(dcoef + (m < n ? m : m - n));
+            }
+        } else {
+            load_dcoef_ext<REPG>(dsh, dcoef, n, K - 2 > 0 ? K - 2 : 0);
+        }
+    }
     __syncthreads();
     if (!(MODE == MODE_PUSH_DEPOSIT && VM_PASS_EARLY_LOAD)) load(A, q);
     if (MODE == MODE_DEPOSIT || (VM_AF_UNROLL && VAR == VAR_AF) || (VM_PRIV_UNROLL && U == 1)) {

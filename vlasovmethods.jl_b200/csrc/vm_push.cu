@@ -327,8 +327,11 @@ void vm_gather_dev(vm_field* f, const double* x_dev, long np, double* e_dev, dou
 // One particle pass with deposition; leaves the LOCAL (this rank's) deposit in f->rhs[0..n).
 // want_solve: also produce phi/dcoef (all-reduce + replicated solve); on a single GPU with a small
 // grid both the reduction and the solve are fused into the pass kernel's last CTA.
+// defer_solve: the caller's next operation on this field is another fused pass (vm_vp_run); on meshes above 128 cells
+// that pass can then do the solve in its own prologue (pass_presolve) instead of k_poisson_solve here.
 static void pass_with_deposit(vm_field* f, vm_particles* p, int pass_mode, int deposit_mode, PassParams P,
-                              bool want_solve, bool prof_deposit = false, double* xsrc = nullptr /* deposit-only: positions to use */)
+                              bool want_solve, bool prof_deposit = false, double* xsrc = nullptr /* deposit-only: positions to use */,
+                              bool defer_solve = false)
 {
     vm_ctx* ctx = f->ctx;
     const int n = f->n;
@@ -383,6 +386,21 @@ static void pass_with_deposit(vm_field* f, vm_particles* p, int pass_mode, int d
         P.repg = pp.repg ? 1 : 0;
     }
     P.rep_log2 = pl.rep_log2;
+    if (f->solve_pending) {
+        // phi / dcoef are one deposit behind: this pass solves in its prologue when it is the limb-atomic fused pass with room
+        // for the scratch (its grids) and a CTA per tile; any other pass gets the separate kernel first
+        const int tiles = (n + 31) / 32;
+        const bool can = af && pass_mode == MODE_PUSH_DEPOSIT && pl.threads >= 256 && pl.grid >= tiles && !ctx->no_fuse &&
+                         vm_af_core_doubles(n, f->order, pl.rep_log2) >= (size_t)VM_SOLVE_SCRATCH_DOUBLES(n);
+        if (can) {
+            f->solve_target += (unsigned)tiles;
+            P.ps_tiles = tiles; P.ps_target = f->solve_target; P.ps_count = f->solve_count; P.ps_err = f->solve_count + 1;
+            P.ps_rhs = f->rhs; P.ps_G = f->G; P.ps_phi = f->phi; P.ps_dcoef = f->dcoef;
+            f->solve_pending = false;
+        } else {
+            vm_field_solve_local(f, false);
+        }
+    }
     FinishParams F{};
     F.mode = FINISH_NONE;
     double* out;
@@ -430,7 +448,12 @@ static void pass_with_deposit(vm_field* f, vm_particles* p, int pass_mode, int d
     if (prof) vm_prof_mark(ctx);
     if (pl.var != VAR_ATOMIC && F.mode == FINISH_NONE) vm_field_reduce_rows(f, out, pl.grid, ncols, f->rhs);
     f->rhs_global = (ctx->nranks == 1) || F.xchg;
-    if (want_solve && F.mode != FINISH_REDUCE_SOLVE) vm_field_solve_local(f, true);
+    if (want_solve && F.mode != FINISH_REDUCE_SOLVE) {
+        // (deferred only when rhs already holds the sum over the ranks and the fused finish produced it: the next pass's
+        // prologue then reads it straight away)
+        if (defer_solve && f->rhs_global && F.mode == FINISH_REDUCE && af && !ctx->no_presolve) f->solve_pending = true;
+        else vm_field_solve_local(f, true);
+    }
 }
 
 static void wv_moments(vm_field* f, vm_particles* p)
@@ -633,6 +656,12 @@ int vm_vp_run(vm_field* f, vm_particles* p, double dt, int nsteps, int diag_ever
         vm_field_store_diag(f, row++, chi);
     };
 
+    // a deposit whose solve was left to the next fused pass (solve_pending) must not outlive this call
+    struct SolveGuard {
+        vm_field* f;
+        ~SolveGuard() { try { if (f->solve_pending) vm_field_solve_local(f, false); } catch (...) { f->solve_pending = false; } }
+    } solve_guard{f};
+    auto fused_step = [&](int s) { return s <= nsteps && !frozen && !unfused && !(diag_every > 0 && (s % diag_every == 0)) && s != nsteps; };
     // a rank with an empty shard still runs every pass: it takes part in the exchanges / all-reduces of the others
     if (diag_every > 0) record_diag(false);
     bool staggered = false;   // true: x holds x^n + dt/2 v^n and f holds phi of those positions
@@ -661,7 +690,7 @@ int vm_vp_run(vm_field* f, vm_particles* p, double dt, int nsteps, int diag_ever
             } else {
                 PassParams P{};
                 P.drift1 = hd;
-                pass_with_deposit(f, p, MODE_DRIFT_DEPOSIT, dmode, P, true);
+                pass_with_deposit(f, p, MODE_DRIFT_DEPOSIT, dmode, P, true, false, nullptr, fused_step(s));
             }
             staggered = true;
         }
@@ -680,7 +709,7 @@ int vm_vp_run(vm_field* f, vm_particles* p, double dt, int nsteps, int diag_ever
         } else {
             PassParams P{};
             P.kick = k1; P.kick2 = k2; P.drift1 = hd; P.drift2 = hd;
-            pass_with_deposit(f, p, MODE_PUSH_DEPOSIT, dmode, P, true);
+            pass_with_deposit(f, p, MODE_PUSH_DEPOSIT, dmode, P, true, false, nullptr, fused_step(s + 1));
         }
     }
     if (nrows > 0) {
