@@ -567,6 +567,35 @@ def test_run_diagnostics_cadence_across_chunks(vm, ctx):
     vm.set_default_context(None)
 
 
+# ------------------------------------------------------- in-pass solve -------
+@pytest.mark.parametrize("n", [130, 256, 1000, 1024])
+def test_in_pass_solve_is_bitwise_the_solve_kernel(vm, oracle, rng, n):
+    """Meshes above 128 cells: between fused passes the Poisson solve runs in the prologue of the next pass
+    (pass_presolve) instead of k_poisson_solve.  Same tile routine: trajectories, diagnostics and the final potential
+    have the same bits as with the separate kernel (tuning no_presolve), through runs with and without diagnostic
+    steps in between, and match the oracle."""
+    a, b, k = 0.0, 2 * math.pi / 0.3, 4
+    npart = 60_001
+    x = rng.uniform(a, b, npart); v = rng.standard_normal(npart); w = np.full(npart, (b - a) / npart)
+    S = oracle.periodic_stiffness(a, b, n, k, 0)
+    xo, vo = x.copy(), v.copy()
+    dref = oracle.integrate_vp(xo, vo, w, 0.1, 1.0, 12, 4, a, b, n, k, 0, S)
+    outs = []
+    for no_presolve in (0, 1):
+        c = vm.Context(0)
+        c.set_tuning("no_presolve", no_presolve)
+        fld = vm.DeviceField(c, a, b, k, n, 0)
+        p = vm.DeviceParticles(c, npart)
+        p.upload(x, v, w)
+        d = fld.run(p, 0.1, 12, 4, 0, 1.0)              # fused stretches of 3 steps between diagnostic steps
+        fld.run(p, 0.1, 7, 0, 0, 1.0)                   # and a stretch without any
+        xs, vs_, _ = p.download(w=False)
+        outs.append((d.tobytes(), xs.tobytes(), vs_.tobytes(), fld.coefficients.tobytes()))
+        assert np.allclose(d[:, :3], dref, rtol=1e-10, atol=1e-13), (n, no_presolve)
+        fld.close(); p.close(); c.close()
+    assert outs[0] == outs[1], n
+
+
 # ------------------------------------------------------------- Sobol loads ---
 def test_sobol_bump_on_tail_loads(vm, ctx):
     """draw!(dist, f_x, ::BumpOnTail, ::ImportanceSampling / ::AcceptRejectSampling) (bumpontail.jl:90-121, 43-75) on the
