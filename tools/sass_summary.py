@@ -10,7 +10,7 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent.parent
 BUILD = ROOT / "vlasovmethods.jl_b200" / "csrc" / "build"
 MODES = {0: "deposit", 1: "push+deposit", 2: "drift+deposit"}
-VARS = {0: "lane-private", 1: "match", 2: "atomic", 3: "xor"}
+VARS = {0: "lane-private", 1: "match", 2: "atomic", 3: "xor", 5: "limb-atomic"}
 
 
 def parse_name(sym):
