@@ -375,7 +375,7 @@ static void pass_with_deposit(vm_field* f, vm_particles* p, int pass_mode, int d
         }
         if (!af) bq = want_bankq(ctx, n, deposit_mode) && plan_bq(ctx, n, f->order, pass_mode, P.uw != 0, &bp);
     }
-    if (af) {          // limb atomics: one two-limb grid per CTA
+    if (af) {          // limb atomics: bank-steered two-limb grids shared by the CTA
         pl = afp.pl;
         P.repg = afp.repg ? 1 : 0;
     } else if (bq) {   // bank-sorted pass: one CTA per SM, one replica grid per warp
